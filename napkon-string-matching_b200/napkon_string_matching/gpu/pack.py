@@ -1,0 +1,273 @@
+"""
+Host-side packing of tokenised items into the arrays the CUDA kernels read (north_star "Token
+packing").  numpy only — no per-pair work happens here.
+
+Jaccard operands (``PackedSets``) — one cohort side, CSR over items -> levels -> tokens:
+
+    item_level_off  uint32[n_items+1]   levels of item i are item_level_off[i]:item_level_off[i+1]
+    level_tok_off   uint32[n_levels+1]  tokens of level g are tok[level_tok_off[g]:level_tok_off[g+1]]
+    tok             uint32[n_tok]       token ids, sorted and unique inside a level
+    level_sig       uint64[n_levels]    64-bit token bitset of the level (bit = id if the whole
+                                        vocabulary has <= 64 ids, else a multiplicative hash of id)
+    level_info      uint32[n_levels]    size | min(size - popcount(sig), 255) << 16
+
+Levels are what ``ComparableData.gen_comp_value`` returns for an item
+(/root/reference/napkon_string_matching/types/comparable_data.py:283-285): level j is the token
+set of the last j+1 parts.  Token identity is the exact, case-sensitive string (Q3/Q4).
+
+fuzzy_match operands (``PackedStrings``): per level the string ``fuzzy_match`` would hand to
+``QRatio`` *after* ``join_sorted`` and rapidfuzz's ``default_process`` (Q5/Q6), as one byte per
+code point through an alphabet shared by both sides:
+
+    item_level_off  uint32[n_items+1]
+    level_chr_off   uint32[n_levels+1]
+    chr             uint8[n_chr]        dense alphabet codes (0 .. n_alphabet-1)
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Iterable, List, Sequence, Tuple
+
+import numpy as np
+import pandas as pd
+
+from napkon_string_matching.text.process import default_process, join_sorted
+
+SIG_HASH_MULT = np.uint32(0x9E3779B1)
+MAX_LEVEL_SIZE = 0xFFFF
+MAX_ALPHABET = 255
+
+
+class PackError(ValueError):
+    pass
+
+
+@dataclass
+class PackedSets:
+    item_level_off: np.ndarray
+    level_tok_off: np.ndarray
+    tok: np.ndarray
+    level_sig: np.ndarray
+    level_info: np.ndarray
+    n_vocab: int
+    sig_exact: bool
+    max_levels: int = 0
+
+    @property
+    def n_items(self) -> int:
+        return len(self.item_level_off) - 1
+
+    @property
+    def n_levels(self) -> int:
+        return len(self.level_tok_off) - 1
+
+    def level_sizes(self) -> np.ndarray:
+        return np.diff(self.level_tok_off.astype(np.int64))
+
+    def levels_per_item(self) -> np.ndarray:
+        return np.diff(self.item_level_off.astype(np.int64))
+
+    def nbytes(self) -> int:
+        return sum(a.nbytes for a in (self.item_level_off, self.level_tok_off, self.tok,
+                                      self.level_sig, self.level_info))
+
+    def rows(self, begin: int, end: int) -> "PackedSets":
+        """Items begin:end as an independent pack (used by tests and CPU baselines)."""
+        g0, g1 = int(self.item_level_off[begin]), int(self.item_level_off[end])
+        t0, t1 = int(self.level_tok_off[g0]), int(self.level_tok_off[g1])
+        return PackedSets(
+            (self.item_level_off[begin : end + 1] - np.uint32(g0)).astype(np.uint32),
+            (self.level_tok_off[g0 : g1 + 1] - np.uint32(t0)).astype(np.uint32),
+            self.tok[t0:t1].copy(), self.level_sig[g0:g1].copy(), self.level_info[g0:g1].copy(),
+            self.n_vocab, self.sig_exact, self.max_levels)
+
+
+@dataclass
+class PackedStrings:
+    item_level_off: np.ndarray
+    level_chr_off: np.ndarray
+    chr: np.ndarray
+    n_alphabet: int
+    max_levels: int = 0
+    max_len: int = 0
+
+    @property
+    def n_items(self) -> int:
+        return len(self.item_level_off) - 1
+
+    @property
+    def n_levels(self) -> int:
+        return len(self.level_chr_off) - 1
+
+    def level_lengths(self) -> np.ndarray:
+        return np.diff(self.level_chr_off.astype(np.int64))
+
+    def levels_per_item(self) -> np.ndarray:
+        return np.diff(self.item_level_off.astype(np.int64))
+
+    def nbytes(self) -> int:
+        return self.item_level_off.nbytes + self.level_chr_off.nbytes + self.chr.nbytes
+
+    def rows(self, begin: int, end: int) -> "PackedStrings":
+        g0, g1 = int(self.item_level_off[begin]), int(self.item_level_off[end])
+        c0, c1 = int(self.level_chr_off[g0]), int(self.level_chr_off[g1])
+        return PackedStrings(
+            (self.item_level_off[begin : end + 1] - np.uint32(g0)).astype(np.uint32),
+            (self.level_chr_off[g0 : g1 + 1] - np.uint32(c0)).astype(np.uint32),
+            self.chr[c0:c1].copy(), self.n_alphabet, self.max_levels, self.max_len)
+
+
+# ------------------------------------------------------------------------------------------
+# signatures
+# ------------------------------------------------------------------------------------------
+def signature_bits(ids: np.ndarray, sig_exact: bool) -> np.ndarray:
+    """Bit position (0..63) of every token id."""
+    ids = ids.astype(np.uint32, copy=False)
+    if sig_exact:
+        return ids.astype(np.uint64)
+    with np.errstate(over="ignore"):
+        return ((ids * SIG_HASH_MULT) >> np.uint32(26)).astype(np.uint64)
+
+
+def _segment_or(values: np.ndarray, offsets: np.ndarray) -> np.ndarray:
+    """bitwise-or of values[offsets[g]:offsets[g+1]] for every g (empty segment -> 0)."""
+    n_seg = len(offsets) - 1
+    out = np.zeros(n_seg, dtype=np.uint64)
+    sizes = np.diff(offsets.astype(np.int64))
+    nonempty = np.nonzero(sizes > 0)[0]
+    if len(nonempty):
+        out[nonempty] = np.bitwise_or.reduceat(values, offsets[nonempty].astype(np.int64))
+    return out
+
+
+def finish_sets(item_level_off, level_tok_off, tok, n_vocab: int) -> PackedSets:
+    """Adds signatures / info words to a CSR whose levels are already sorted and unique."""
+    item_level_off = np.ascontiguousarray(item_level_off, dtype=np.uint32)
+    level_tok_off = np.ascontiguousarray(level_tok_off, dtype=np.uint32)
+    tok = np.ascontiguousarray(tok, dtype=np.uint32)
+    sizes = np.diff(level_tok_off.astype(np.int64))
+    if len(sizes) and sizes.max() > MAX_LEVEL_SIZE:
+        raise PackError(f"a level holds {sizes.max()} tokens; the packed format allows 65535")
+    sig_exact = n_vocab <= 64
+    bits = np.left_shift(np.uint64(1), signature_bits(tok, sig_exact))
+    sig = _segment_or(bits, level_tok_off)
+    extra = np.minimum(sizes - np.bitwise_count(sig).astype(np.int64), 255)
+    info = (sizes.astype(np.uint32)) | (extra.astype(np.uint32) << np.uint32(16))
+    k = np.diff(item_level_off.astype(np.int64))
+    return PackedSets(item_level_off, level_tok_off, tok, sig, info.astype(np.uint32),
+                      int(n_vocab), bool(sig_exact), int(k.max()) if len(k) else 0)
+
+
+def _csr_from_nested(items_levels: Sequence[Sequence[Sequence]]) -> Tuple[np.ndarray, np.ndarray, list]:
+    k = np.fromiter((len(lv) for lv in items_levels), dtype=np.int64, count=len(items_levels))
+    item_level_off = np.zeros(len(k) + 1, dtype=np.int64)
+    np.cumsum(k, out=item_level_off[1:])
+    sizes, flat = [], []
+    for lv in items_levels:
+        for level in lv:
+            if isinstance(level, str):  # intersection_vs_union splits a str operand
+                level = level.split()
+            sizes.append(len(level))
+            flat.extend(level)
+    level_off = np.zeros(len(sizes) + 1, dtype=np.int64)
+    np.cumsum(np.asarray(sizes, dtype=np.int64), out=level_off[1:])
+    return item_level_off, level_off, flat
+
+
+def _sort_unique_levels(level_off: np.ndarray, codes: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """Sort ids inside every level and drop duplicates (the score function works on sets)."""
+    n_levels = len(level_off) - 1
+    sizes = np.diff(level_off)
+    level_id = np.repeat(np.arange(n_levels, dtype=np.int64), sizes)
+    order = np.lexsort((codes, level_id))
+    codes, level_id = codes[order], level_id[order]
+    keep = np.ones(len(codes), dtype=bool)
+    if len(codes) > 1:
+        keep[1:] = (codes[1:] != codes[:-1]) | (level_id[1:] != level_id[:-1])
+    codes, level_id = codes[keep], level_id[keep]
+    new_sizes = np.bincount(level_id, minlength=n_levels).astype(np.int64)
+    new_off = np.zeros(n_levels + 1, dtype=np.int64)
+    np.cumsum(new_sizes, out=new_off[1:])
+    return new_off, codes
+
+
+def pack_sets(*sides: Sequence[Sequence[Sequence[str]]]) -> List[PackedSets]:
+    """Dictionary-encodes the token strings of all ``sides`` together (exact string identity)
+    and packs each side.  ``sides[s][i][j]`` is the token list of level j of item i."""
+    parts = [_csr_from_nested(s) for s in sides]
+    all_tokens = [t for _, _, flat in parts for t in flat]
+    if all_tokens:
+        codes_all, uniques = pd.factorize(np.asarray(all_tokens, dtype=object))
+        n_vocab = len(uniques)
+    else:
+        codes_all, n_vocab = np.zeros(0, dtype=np.int64), 0
+    out, pos = [], 0
+    for item_level_off, level_off, flat in parts:
+        codes = codes_all[pos : pos + len(flat)].astype(np.int64)
+        pos += len(flat)
+        new_off, codes = _sort_unique_levels(level_off, codes)
+        out.append(finish_sets(item_level_off, new_off, codes, n_vocab))
+    return out
+
+
+def pack_suffix_id_sets(lens: np.ndarray, flat_ids: np.ndarray, n_vocab: int) -> PackedSets:
+    """Integer fast path for list-valued columns whose parts are single tokens (``TokenIds``):
+    item i has the id list ``v = flat_ids[o_i : o_i + lens[i]]`` and level j is ``set(v[-(j+1):])``
+    (Q2), built without Python loops."""
+    lens = np.asarray(lens, dtype=np.int64)
+    n = len(lens)
+    item_end = np.cumsum(lens)
+    item_level_off = np.zeros(n + 1, dtype=np.int64)
+    item_level_off[1:] = item_end  # one level per list element
+    n_levels = int(item_end[-1]) if n else 0
+    level_item = np.repeat(np.arange(n, dtype=np.int64), lens)
+    level_j = np.arange(n_levels, dtype=np.int64) - np.repeat(item_end - lens, lens)
+    raw_sizes = level_j + 1
+    raw_off = np.zeros(n_levels + 1, dtype=np.int64)
+    np.cumsum(raw_sizes, out=raw_off[1:])
+    # element e of level (i, j) is v[len_i - 1 - j + e]
+    within = np.arange(int(raw_off[-1]), dtype=np.int64) - np.repeat(raw_off[:-1], raw_sizes)
+    src = np.repeat(item_end[level_item] - 1 - level_j, raw_sizes) + within
+    codes = np.asarray(flat_ids, dtype=np.int64)[src]
+    new_off, codes = _sort_unique_levels(raw_off, codes)
+    return finish_sets(item_level_off, new_off, codes, n_vocab)
+
+
+# ------------------------------------------------------------------------------------------
+# strings
+# ------------------------------------------------------------------------------------------
+def fuzzy_level_strings(items_levels: Sequence[Sequence]) -> List[List[str]]:
+    """Per level: ``default_process(join_sorted(tokens))`` (or of the str itself)."""
+    return [[default_process(join_sorted(level) if isinstance(level, list) else level)
+             for level in lv] for lv in items_levels]
+
+
+def pack_strings(*sides: Sequence[Sequence[str]]) -> List[PackedStrings]:
+    """``sides[s][i][j]`` is the already processed string of level j of item i."""
+    per_side = []
+    for s in sides:
+        k = np.fromiter((len(lv) for lv in s), dtype=np.int64, count=len(s))
+        strs = [x for lv in s for x in lv]
+        lens = np.fromiter((len(x) for x in strs), dtype=np.int64, count=len(strs))
+        cps = np.frombuffer("".join(strs).encode("utf-32-le"), dtype=np.uint32)
+        per_side.append((k, lens, cps))
+    alphabet = np.unique(np.concatenate([c for _, _, c in per_side])) if per_side else np.zeros(0)
+    if len(alphabet) > MAX_ALPHABET:
+        raise PackError(f"{len(alphabet)} distinct code points; the packed format allows 255")
+    out = []
+    for k, lens, cps in per_side:
+        item_level_off = np.zeros(len(k) + 1, dtype=np.int64)
+        np.cumsum(k, out=item_level_off[1:])
+        level_chr_off = np.zeros(len(lens) + 1, dtype=np.int64)
+        np.cumsum(lens, out=level_chr_off[1:])
+        codes = np.searchsorted(alphabet, cps).astype(np.uint8)
+        out.append(PackedStrings(item_level_off.astype(np.uint32), level_chr_off.astype(np.uint32),
+                                 np.ascontiguousarray(codes), int(len(alphabet)),
+                                 int(k.max()) if len(k) else 0,
+                                 int(lens.max()) if len(lens) else 0))
+    return out
+
+
+def flat_items(values: Iterable) -> List[list]:
+    """K = 1 items for the flat (scalar ``score_func``) entry points."""
+    return [[v] for v in values]
