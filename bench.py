@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""
+bench.py — the reference's headline metric on B200: item pair-scores/sec (scored + thresholded).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" is one pass of the comparison hot path over one batch of synthetic cohorts:
+the workload `tokenids50k` (BASELINE.json configs[1]) scores HAP x POP, HAP x SUEP and POP x SUEP,
+50 000 items per cohort, `intersection_vs_union` on the `TokenIds` column, score_threshold 0.1.
+A pair-score is one `score_func` evaluation that compare_terms asks for (max(K_left, K_right)
+per item pair), either computed exactly or proven to belong to a pair below the threshold.
+
+N > 1 (launched by torchrun, one rank per GPU): every rank scores its own left row block of the
+same size against the replicated right cohort (weak scaling, no data-path collective); the only
+collective is the NCCL all-gather of the per-rank kept-pair counts.
+
+`--impl reference` times the CPU restatement of the reference's own Python pair loop
+(oracle/reference_port.py, all host cores through multiprocessing) on a bounded sample of the
+same workload; the reference itself is Python and /root/reference does not exist on the GPU box.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import pathlib
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT / "napkon-string-matching_b200"))
+sys.path.insert(0, str(ROOT))
+
+METRIC = "item pair-scores/sec (scored+thresholded)"
+UNIT = "pair-scores/s"
+
+WORKLOADS = {
+    # name: (kind, items per cohort, threshold)
+    "tokenids50k": dict(kind="tokenids", n=50_000, thr=0.1,
+                        desc="HAPxPOPxSUEP, 50k items/cohort, intersection_vs_union on TokenIds, thr 0.1"),
+    "tokenids5k": dict(kind="tokenids", n=5_000, thr=0.1, desc="reduced tokenids (debug)"),
+    "fuzzy20k": dict(kind="fuzzy", n=20_000, thr=0.7,
+                     desc="fuzzy_match flat strings 20k x 20k, avg 60 chars, thr 0.7"),
+}
+
+
+# ------------------------------------------------------------------------------------------
+# workload construction (host, outside every timed region)
+# ------------------------------------------------------------------------------------------
+def build_tokenids(n: int, rank: int):
+    from napkon_string_matching import synthetic as syn
+    from napkon_string_matching.gpu import pack
+
+    seeds = {"hap": syn.SEED_LEFT, "pop": syn.SEED_RIGHT, "suep": syn.SEED_THIRD}
+    packs, raw = {}, {}
+    for name, seed in seeds.items():
+        lens, flat = syn.token_id_level_sets(n, seed + 1000 * rank)
+        raw[name] = (lens, flat)
+        packs[name] = pack.pack_suffix_id_sets(lens, flat, 30000)
+    pairs = [("hap", "pop"), ("hap", "suep"), ("pop", "suep")]
+    return packs, raw, pairs
+
+
+def build_fuzzy(n: int, rank: int):
+    from napkon_string_matching import synthetic as syn
+    from napkon_string_matching.gpu import pack
+    from napkon_string_matching.text.process import default_process
+
+    vocab = syn.vocabulary()
+    sl = [[default_process(s)] for s in syn.question_strings(n, syn.SEED_LEFT + 1000 * rank, vocab)]
+    sr = [[default_process(s)] for s in syn.question_strings(n, syn.SEED_RIGHT + 1000 * rank, vocab)]
+    pl, pr = pack.pack_strings(sl, sr)
+    return {"left": pl, "right": pr}, {"left": sl, "right": sr}, [("left", "right")]
+
+
+def schedule_counts(left, right):
+    """(evals, algorithmic int32 ops) of one comparison, in closed form from the packs.
+
+    evals = sum over item pairs of max(K_l, K_r) (compare_terms, comparable_data.py:261).
+    ops   = SURVEY.md §8(d): a + b per Jaccard evaluation (|A| + |B| of the two level sets),
+            8 * ceil(m/64) * n per fuzzy evaluation (m = shorter string)."""
+    kl, kr = left.levels_per_item(), right.levels_per_item()
+    kmax = int(max(kl.max(initial=0), kr.max(initial=0)))
+    hist_r = np.bincount(kr, minlength=kmax + 1).astype(np.float64)
+    hist_l = np.bincount(kl, minlength=kmax + 1).astype(np.float64)
+    ks = np.arange(kmax + 1)
+    evals = float((np.maximum.outer(ks, ks) * np.outer(hist_l, hist_r))[1:, 1:].sum())
+    if not hasattr(left, "tok"):
+        # flat strings: one evaluation per pair
+        ll, lr = left.level_lengths().astype(np.float64), right.level_lengths().astype(np.float64)
+        # sum over pairs of 8 * ceil(min/64) * max  (exact for lengths <= 64: 8 * max(m, n))
+        a = np.sort(ll)
+        ops = 0.0
+        for chunk in np.array_split(lr, max(1, len(lr) // 4096)):
+            mn = np.minimum.outer(a, chunk)
+            mx = np.maximum.outer(a, chunk)
+            ops += float((8.0 * np.ceil(mn / 64.0) * mx).sum())
+        return float(len(ll)) * float(len(lr)), ops
+
+    def cum_sizes(p, k_items):
+        """S[i, T] = sum_{t=1..T} size(level min(t, K_i - 1)) for T = 0..kmax."""
+        sizes = p.level_sizes()
+        off = p.item_level_off.astype(np.int64)
+        out = np.zeros((p.n_items, kmax + 1))
+        for t in range(1, kmax + 1):
+            idx = off[:-1] + np.minimum(t, np.maximum(k_items - 1, 0))
+            out[:, t] = out[:, t - 1] + np.where(k_items > 0, sizes[np.minimum(idx, len(sizes) - 1)], 0)
+        return out
+
+    sl, sr = cum_sizes(left, kl), cum_sizes(right, kr)
+    ops = 0.0
+    for k in range(1, kmax + 1):  # right items with K_r == k
+        if hist_r[k]:
+            ops += hist_r[k] * float(sl[np.arange(left.n_items), np.maximum(kl, k)].sum())
+        if hist_l[k]:
+            ops += hist_l[k] * float(sr[np.arange(right.n_items), np.maximum(kr, k)].sum())
+    return evals, ops
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-i", str(self.gpu_index), "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15 and len(r) >= 9] or \
+               [r for _, r in self.rows if len(r) >= 9]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in rows for n, v in zip(names, r[5:9]) if v.lower() == "active"})
+        num = lambda s: float(s) if s.replace(".", "", 1).isdigit() else None
+        sm = [num(r[1]) for r in rows if num(r[1]) is not None]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": num(rows[0][2]),
+                "reasons": reasons, "samples": len(rows),
+                "power_w_max": max((num(r[3]) or 0.0) for r in rows)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU reference arm (oracle port of the reference's Python pair loop)
+# ------------------------------------------------------------------------------------------
+def _levels_from_ids(lens, flat, begin, end):
+    """String level lists of items begin:end, exactly what gen_comp_value yields for TokenIds."""
+    starts = np.concatenate([[0], np.cumsum(lens)])
+    out = []
+    for i in range(begin, end):
+        ids = [f"D{int(v):06d}" for v in flat[starts[i]:starts[i + 1]]]
+        out.append([sorted(set(ids[-j:])) for j in range(1, len(ids) + 1)])
+    return out
+
+
+def _cpu_block(args):
+    from oracle import reference_port as port
+
+    left, right, func, thr = args
+    t0 = time.perf_counter()
+    kept = port.all_pairs(left, right, func, thr)
+    evals = sum(max(len(a), len(b)) for a in left for b in right)
+    return len(kept), evals, time.perf_counter() - t0
+
+
+def cpu_reference(workload: dict, raw, pairs, seconds: float, procs: int):
+    """Times oracle/reference_port.all_pairs on left row blocks of the first comparison until
+    about `seconds` of wall time are used.  Returns (pair-scores/s, sample description)."""
+    import multiprocessing as mp
+
+    a, b = pairs[0]
+    n_right = 1000 if workload["kind"] == "tokenids" else 250
+    rows_per_block = 40 if workload["kind"] == "tokenids" else 10
+    if workload["kind"] == "tokenids":
+        func = "intersection_vs_union"
+        right = _levels_from_ids(*raw[b], 0, n_right)
+        block = lambda i: _levels_from_ids(*raw[a], i * rows_per_block, (i + 1) * rows_per_block)
+    else:
+        func = "fuzzy_match"
+        # K = 1 items: compare_terms halves the flat score, so the port's threshold is thr / 2
+        right = [[s] for (s,) in raw[b][:n_right]]
+        block = lambda i: [[s] for (s,) in raw[a][i * rows_per_block:(i + 1) * rows_per_block]]
+    thr = workload["thr"] if workload["kind"] == "tokenids" else workload["thr"] / 2
+    done_evals = done_pairs = n_blocks = 0
+    t_start = time.perf_counter()
+    with mp.get_context("fork").Pool(procs) as pool:
+        nxt = 0
+        while time.perf_counter() - t_start < seconds:
+            jobs = [(block(nxt + j), right, func, thr) for j in range(procs)]
+            nxt += procs
+            for kept, evals, _ in pool.map(_cpu_block, jobs):
+                done_evals += evals
+                done_pairs += rows_per_block * n_right
+            n_blocks += procs
+    wall = time.perf_counter() - t_start
+    sample = (f"{n_blocks * rows_per_block} x {n_right} items of {a} x {b} "
+              f"({done_pairs} item pairs, {done_evals} pair-scores) through "
+              f"oracle/reference_port.all_pairs, {procs} processes, {wall:.1f} s wall")
+    return done_evals / wall, sample
+
+
+def run_reference_arm(args, rank: int):
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    procs = os.cpu_count() or 1
+    build = build_tokenids if wl["kind"] == "tokenids" else build_fuzzy
+    n_small = min(wl["n"], 20000)
+    packs, raw, pairs = build(n_small, 0)
+    per_step = max(5.0, min(20.0, 90.0 / max(1, args.steps + args.warmup)))
+    vals = []
+    sample = ""
+    for i in range(args.warmup + args.steps):
+        v, sample = cpu_reference(wl, raw, pairs, per_step, procs)
+        if i >= args.warmup:
+            vals.append(v)
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32+f64" if wl["kind"] == "tokenids" else "u64+f64", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": wl["desc"]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args, rank: int, world: int, local_rank: int):
+    import torch
+    import torch.distributed as dist
+
+    from napkon_string_matching.gpu.engine import Engine
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    wl = WORKLOADS[args.workload]
+    build = build_tokenids if wl["kind"] == "tokenids" else build_fuzzy
+    packs, raw, pairs = build(wl["n"], rank)
+    flat = wl["kind"] == "fuzzy"
+    thr = wl["thr"]
+
+    eng = Engine()
+    pinned = {k: eng.pin(p) for k, p in packs.items()}
+    counts = [schedule_counts(packs[a], packs[b]) for a, b in pairs]
+    evals_step = sum(c[0] for c in counts)
+    ops_step = sum(c[1] for c in counts)
+    item_pairs_step = sum(packs[a].n_items * packs[b].n_items for a, b in pairs)
+    in_bytes = sum(p.nbytes() for p in packs.values())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.current_stream()
+    dev = {k: eng.upload(p, pinned[k]) for k, p in packs.items()}
+    torch.cuda.synchronize()
+
+    def step_resident():
+        kept = 0
+        for a, b in pairs:
+            eng.all_pairs(dev[a], dev[b], thr, flat=flat, to_host=False)
+            kept += eng.last_info["count"]
+        return kept
+
+    def step_e2e():
+        d = {k: eng.upload(p, pinned[k]) for k, p in packs.items()}
+        kept = d2h = 0
+        for a, b in pairs:
+            out = eng.all_pairs(d[a], d[b], thr, flat=flat, to_host=True, copy=False)
+            kept += len(out)
+            d2h += eng.last_info["d2h_bytes"]
+        return kept, d2h
+
+    # ---- kernel-resident timing (value) -------------------------------------------------
+    for _ in range(max(3, args.warmup)):
+        kept = step_resident()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    launches0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record(stream)
+    for _ in range(args.steps):
+        kept = step_resident()
+    e1.record(stream)
+    barrier()
+    t1 = time.time()
+    launches = eng.launches - launches0
+    ms = e0.elapsed_time(e1)
+    stats = dict(eng.last_info["stats"])
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+
+    # ---- end-to-end timing (host packs -> host records) ---------------------------------
+    for _ in range(max(3, args.warmup)):
+        step_e2e()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(stream)
+    for _ in range(args.steps):
+        kept_e2e, d2h = step_e2e()
+    f1.record(stream)
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([kept], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gathered = [torch.zeros_like(cnt) for _ in range(world)]
+        dist.all_gather(gathered, cnt)  # the path's one collective: kept-pair counts
+        kept_all = [int(g.item()) for g in gathered]
+    else:
+        kept_all = [kept]
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        except OSError:
+            pass
+        int_peaks = {name: eng.microbench(kind) for kind, name in
+                     enumerate(("lop3", "iadd3", "popc", "lcs_step_u64"))}
+        peak_ops = max(int_peaks["lop3"], int_peaks["iadd3"])
+        sec_step = ms * 1e-3 / args.steps
+        value = evals_step * world / sec_step
+        achieved = ops_step / sec_step
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        alg_bytes = in_bytes + 16 * kept
+        cpu_val, cpu_sample = cpu_reference(wl, raw, pairs, 12.0, 1)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32+f64" if wl["kind"] == "tokenids" else "u64+f64", "data": "synthetic",
+            "config": {"workload": args.workload, "desc": wl["desc"],
+                       "item_pairs_per_step_per_gpu": item_pairs_step,
+                       "pair_scores_per_step_per_gpu": evals_step,
+                       "kept_pairs_per_step": kept_all,
+                       "l2": "inputs are re-streamed from HBM/L2 by design (all-pairs reuse); "
+                             "output records (%.0f MB/step) exceed L2" % (16e-6 * kept)},
+            "item_pairs_per_s": item_pairs_step * world / sec_step,
+            "roofline": {"bound": "int32_alu", "achieved": achieved / 1e12, "peak": peak_ops / 1e12,
+                         "unit": "Tiop/s", "frac": achieved / peak_ops, "traffic": None,
+                         "peak_source": "nsm_microbench measured in this run (LOP3/IADD3 stream)",
+                         "alg_ops_per_step": ops_step},
+            "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / sec_step / 1e9,
+                             "peak": hbm_peak, "unit": "GB/s",
+                             "frac": alg_bytes / sec_step / 1e9 / hbm_peak,
+                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+            "int_peaks_tiops": {k: v / 1e12 for k, v in int_peaks.items()},
+            "kernel_stats_last_launch": stats,
+            "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": cpu_sample},
+            "e2e": {"value": evals_step * world / (ms_e2e * 1e-3 / args.steps), "unit": UNIT,
+                    "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": in_bytes,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="tokenids50k", choices=sorted(WORKLOADS))
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,131 @@
+/*
+ * nsm.h — C ABI of the B200-native cross-cohort comparison path (libnsm_b200.so).
+ *
+ * The reference (BIH-CEI/napkon-string-matching) is pure Python and has no FFI; the seam this
+ * library sits behind is the body of
+ *     ComparableData.gen_comparable      napkon_string_matching/types/comparable_data.py:223-243
+ * i.e. "for every (left item, right item) of the cross product (:191): compare_terms(...)
+ * (:248-265) with score_func = intersection_vs_union | fuzzy_match
+ * (compare/score_functions.py:6-27), keep MatchScore >= score_threshold (:243)".
+ * INTEGRATION.md shows the ctypes stub a maintainer of the reference would add at that point.
+ *
+ * Conventions
+ *  - Every pointer inside nsm_sets_t / nsm_strings_t / nsm_job_t is a DEVICE pointer on the
+ *    current CUDA device.  The library never allocates, frees or retains caller-visible memory;
+ *    it keeps no state besides a thread-local error string.
+ *  - Calls enqueue work on `stream` (a cudaStream_t passed as void*) and return without
+ *    synchronising.  out_count / out_flags / out_stats are zeroed on the stream first; read
+ *    them after synchronising the stream.
+ *  - Return value: NSM_OK or an NSM_ERR_* code; nsm_last_error() gives the text.  Nothing throws.
+ *  - There is no CPU implementation behind these entry points.
+ */
+#ifndef NSM_H_
+#define NSM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSM_VERSION 100 /* 0.1.0 */
+
+/* return codes */
+#define NSM_OK 0
+#define NSM_ERR_BAD_ARG 1
+#define NSM_ERR_CUDA 2
+#define NSM_ERR_UNSUPPORTED 3
+
+/* bits of *out_flags */
+#define NSM_FLAG_OVERFLOW 1u   /* more pairs kept than out_capacity (count is still exact) */
+#define NSM_FLAG_ZERO_UNION 2u /* an evaluated level pair had two empty sets: the reference raises
+                                  ZeroDivisionError (score_functions.py:13); pair not emitted */
+#define NSM_FLAG_EMPTY_ITEM 4u /* an item without levels met one with levels: the reference raises
+                                  IndexError (comparable_data.py:262); pair not emitted */
+
+/* cat_mode: categories_matching, comparable_data.py:464-476 */
+#define NSM_CAT_OFF 0
+#define NSM_CAT_LIST_LIST 1 /* keep if masks intersect or both are empty */
+#define NSM_CAT_MEMBER 2    /* keep if masks intersect (x in set(y), x == y) */
+
+/* One kept pair: positions in the left / right cohort and the float64 MatchScore. */
+typedef struct nsm_pair {
+    uint32_t left;
+    uint32_t right;
+    double score;
+} nsm_pair_t;
+
+/* One cohort side for intersection_vs_union: CSR items -> levels -> sorted unique token ids
+ * (layout and meaning: napkon_string_matching/gpu/pack.py).  Levels are what
+ * ComparableData.gen_comp_value returns per item (comparable_data.py:283-285). */
+typedef struct nsm_sets {
+    const uint32_t *item_level_off; /* [n_items + 1] */
+    const uint32_t *level_tok_off;  /* [n_levels + 1] */
+    const uint32_t *tok;            /* [level_tok_off[n_levels]] */
+    const uint64_t *level_sig;      /* [n_levels] 64-bit token bitset (exact iff sig_exact) */
+    const uint32_t *level_info;     /* [n_levels] size | min(size - popc(sig), 255) << 16 */
+    uint32_t n_items;
+    uint32_t n_levels;
+    uint32_t max_levels; /* max levels of any item on this side */
+    uint32_t sig_exact;  /* 1: vocabulary <= 64 ids, bit == id, popc(sig & sig) is the intersection */
+} nsm_sets_t;
+
+/* One cohort side for fuzzy_match: per level the processed string QRatio sees
+ * (join_sorted + default_process, score_functions.py:16-27), one alphabet code per code point. */
+typedef struct nsm_strings {
+    const uint32_t *item_level_off; /* [n_items + 1] */
+    const uint32_t *level_chr_off;  /* [n_levels + 1] */
+    const uint8_t *chr;             /* [level_chr_off[n_levels]] codes < n_alphabet */
+    uint32_t n_items;
+    uint32_t n_levels;
+    uint32_t max_levels;
+    uint32_t max_len;    /* longest level string on this side */
+    uint32_t n_alphabet; /* shared by both sides, <= 255 */
+} nsm_strings_t;
+
+/* What to compare and where the kept pairs go. */
+typedef struct nsm_job {
+    uint32_t l_row_begin; /* left items [l_row_begin, l_row_end) x all right items: the row block */
+    uint32_t l_row_end;   /*   one GPU owns (multi-GPU partitioning is by left row blocks) */
+    uint32_t flat;        /* 0: compare_terms over levels (weights 2^-i, index from 1);
+                             1: items have one level, score = score_func(level0, level0) */
+    uint32_t cat_mode;    /* NSM_CAT_* ; masks below may be NULL when NSM_CAT_OFF */
+    double threshold;     /* keep score >= threshold (float64 compare, comparable_data.py:243) */
+    const uint64_t *l_cat; /* [left.n_items] category bit masks */
+    const uint64_t *r_cat; /* [right.n_items] */
+    nsm_pair_t *out_pairs; /* [out_capacity], filled densely in no particular order */
+    uint64_t out_capacity;
+    uint64_t *out_count; /* number of kept pairs, also beyond capacity */
+    uint32_t *out_flags; /* NSM_FLAG_* */
+    uint64_t *out_stats; /* optional [NSM_N_STATS] counters, may be NULL */
+} nsm_job_t;
+
+#define NSM_STAT_CANDIDATES 0 /* item pairs that reached exact scoring */
+#define NSM_STAT_LEVEL_EVALS 1 /* score_func evaluations done exactly (merge / LCS) */
+#define NSM_STAT_LEVEL_MERGES 2 /* of those, ones that needed a token merge */
+#define NSM_N_STATS 4
+
+int nsm_version(void);
+const char *nsm_last_error(void);
+
+/* Replaces the pair loop of gen_comparable (comparable_data.py:223-243) for
+ * score_func == "intersection_vs_union" (score_functions.py:6-13). */
+int nsm_jaccard_allpairs(const nsm_sets_t *left, const nsm_sets_t *right, const nsm_job_t *job,
+                         void *stream);
+
+/* Same for score_func == "fuzzy_match" (score_functions.py:20-27; rapidfuzz QRatio/100 as the
+ * normalised Indel similarity, bit-parallel LCS). */
+int nsm_qratio_allpairs(const nsm_strings_t *left, const nsm_strings_t *right, const nsm_job_t *job,
+                        void *stream);
+
+/* Integer-pipe micro-benchmarks used as roofline denominators: every thread of
+ * a blocks x threads grid runs `iters` rounds of 8 independent chains x 4 dependent ops of
+ * `kind` (0: LOP3, 1: IADD3, 2: POPC, 3: 64-bit add/sub/and/or LCS step).  *ops_per_thread
+ * receives the number of 32-bit integer ops one thread executed.  Time it with CUDA events. */
+int nsm_microbench(int kind, uint32_t blocks, uint32_t threads, uint32_t iters, uint32_t *sink,
+                   uint64_t *ops_per_thread, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NSM_H_ */

@@ -1,0 +1,48 @@
+"""Builds csrc/*.cu into napkon_string_matching/gpu/libnsm_b200.so for sm_100a (in-tree, so the
+library travels with the repository snapshot).  `python build.py [--force]`."""
+from __future__ import annotations
+
+import pathlib
+import subprocess
+import sys
+
+HERE = pathlib.Path(__file__).resolve().parent
+CSRC = HERE / "csrc"
+INCLUDE = HERE.parent / "include"
+OUT = HERE / "napkon_string_matching" / "gpu" / "libnsm_b200.so"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "--shared", "-Xcompiler", "-fPIC",
+    "-Xptxas", "-v",
+    "-I", str(INCLUDE), "-I", str(CSRC),
+]
+
+
+def sources():
+    return sorted(CSRC.glob("*.cu"))
+
+
+def needs_build() -> bool:
+    if not OUT.exists():
+        return True
+    newest = max(p.stat().st_mtime for p in [*CSRC.iterdir(), *INCLUDE.glob("*.h")])
+    return newest > OUT.stat().st_mtime
+
+
+def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
+    if not force and not needs_build():
+        return OUT
+    cmd = ["nvcc", *NVCC_FLAGS, "-o", str(OUT), *map(str, sources())]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode:
+        sys.stderr.write(res.stdout + res.stderr)
+    if res.returncode:
+        raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    (HERE / "build.log").write_text(res.stdout + res.stderr)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

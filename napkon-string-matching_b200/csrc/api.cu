@@ -1,0 +1,71 @@
+// Entry points that are not kernels: version, error text, job validation, device facts.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "nsm_common.cuh"
+
+namespace nsm {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count() {
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            cached = n;
+        else
+            cached = 148;
+    }
+    return cached;
+}
+
+float filter_threshold(double threshold) {
+    if (isnan(threshold)) return nanf("");
+    if (!(threshold > 0.0)) return -INFINITY;
+    // the float64 accumulation can exceed the real-valued sum by a few ulp; 1e-9 relative slack
+    // covers that by many orders of magnitude, then step one fp32 value down so the conversion's
+    // own rounding cannot lift the bound
+    const float f = (float)(threshold * (1.0 - 1e-9));
+    return nextafterf(f, -INFINITY);
+}
+
+int prepare_job(const nsm_job_t *job, uint32_t n_left, cudaStream_t stream) {
+    if (job->l_row_begin > job->l_row_end || job->l_row_end > n_left) {
+        set_error("row block [%u, %u) outside the %u left items", job->l_row_begin, job->l_row_end,
+                  n_left);
+        return NSM_ERR_BAD_ARG;
+    }
+    if (!job->out_count || !job->out_flags || (job->out_capacity && !job->out_pairs)) {
+        set_error("out_count / out_flags / out_pairs must be device pointers");
+        return NSM_ERR_BAD_ARG;
+    }
+    if (job->cat_mode > NSM_CAT_MEMBER || (job->cat_mode && (!job->l_cat || !job->r_cat))) {
+        set_error("bad category mode or missing category masks");
+        return NSM_ERR_BAD_ARG;
+    }
+    if (reinterpret_cast<uintptr_t>(job->out_pairs) & 15u) {
+        set_error("out_pairs must be 16-byte aligned");
+        return NSM_ERR_BAD_ARG;
+    }
+    NSM_CUDA_CHECK(cudaMemsetAsync(job->out_count, 0, sizeof(uint64_t), stream));
+    NSM_CUDA_CHECK(cudaMemsetAsync(job->out_flags, 0, sizeof(uint32_t), stream));
+    if (job->out_stats)
+        NSM_CUDA_CHECK(cudaMemsetAsync(job->out_stats, 0, NSM_N_STATS * sizeof(uint64_t), stream));
+    return NSM_OK;
+}
+
+}  // namespace nsm
+
+extern "C" int nsm_version(void) { return NSM_VERSION; }
+
+extern "C" const char *nsm_last_error(void) { return nsm::g_error; }

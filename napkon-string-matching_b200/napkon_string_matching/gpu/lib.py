@@ -1,0 +1,78 @@
+"""ctypes binding of libnsm_b200.so (include/nsm.h).  There is no CPU implementation behind it:
+if the library or a CUDA device is missing, loading raises."""
+from __future__ import annotations
+
+import ctypes as C
+import pathlib
+
+import numpy as np
+
+_HERE = pathlib.Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libnsm_b200.so"
+
+NSM_OK = 0
+FLAG_OVERFLOW, FLAG_ZERO_UNION, FLAG_EMPTY_ITEM = 1, 2, 4
+CAT_OFF, CAT_LIST_LIST, CAT_MEMBER = 0, 1, 2
+N_STATS = 4
+STAT_NAMES = ("candidates", "level_evals", "level_merges", "reserved")
+
+PAIR_DTYPE = np.dtype([("left", np.uint32), ("right", np.uint32), ("score", np.float64)])
+assert PAIR_DTYPE.itemsize == 16
+
+EXPORTS = ("nsm_version", "nsm_last_error", "nsm_jaccard_allpairs", "nsm_qratio_allpairs",
+           "nsm_microbench")
+
+
+class NsmSets(C.Structure):
+    _fields_ = [("item_level_off", C.c_void_p), ("level_tok_off", C.c_void_p),
+                ("tok", C.c_void_p), ("level_sig", C.c_void_p), ("level_info", C.c_void_p),
+                ("n_items", C.c_uint32), ("n_levels", C.c_uint32), ("max_levels", C.c_uint32),
+                ("sig_exact", C.c_uint32)]
+
+
+class NsmStrings(C.Structure):
+    _fields_ = [("item_level_off", C.c_void_p), ("level_chr_off", C.c_void_p),
+                ("chr", C.c_void_p), ("n_items", C.c_uint32), ("n_levels", C.c_uint32),
+                ("max_levels", C.c_uint32), ("max_len", C.c_uint32), ("n_alphabet", C.c_uint32)]
+
+
+class NsmJob(C.Structure):
+    _fields_ = [("l_row_begin", C.c_uint32), ("l_row_end", C.c_uint32), ("flat", C.c_uint32),
+                ("cat_mode", C.c_uint32), ("threshold", C.c_double), ("l_cat", C.c_void_p),
+                ("r_cat", C.c_void_p), ("out_pairs", C.c_void_p), ("out_capacity", C.c_uint64),
+                ("out_count", C.c_void_p), ("out_flags", C.c_void_p), ("out_stats", C.c_void_p)]
+
+
+class NsmError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Loads the CUDA library.  Raises if it has not been built (python build.py)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise NsmError(
+            f"{LIB_PATH} is missing: build it with `python napkon-string-matching_b200/build.py` "
+            "(there is no CPU fallback for the comparison path)")
+    lib = C.CDLL(str(LIB_PATH))
+    lib.nsm_version.restype = C.c_int
+    lib.nsm_last_error.restype = C.c_char_p
+    for name, first in (("nsm_jaccard_allpairs", NsmSets), ("nsm_qratio_allpairs", NsmStrings)):
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = [C.POINTER(first), C.POINTER(first), C.POINTER(NsmJob), C.c_void_p]
+    lib.nsm_microbench.restype = C.c_int
+    lib.nsm_microbench.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
+                                   C.POINTER(C.c_uint64), C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != NSM_OK:
+        raise NsmError(f"nsm error {rc}: {load().nsm_last_error().decode(errors='replace')}")

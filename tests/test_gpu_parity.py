@@ -1,0 +1,196 @@
+"""GPU suite: the CUDA path (through the C ABI) against the oracle and the reference-generated
+golden vectors.  Bit-exact: same pair set, same float64 scores."""
+import numpy as np
+import pytest
+
+from conftest import assert_same_triples, load_golden
+from oracle import c_oracle
+from napkon_string_matching import synthetic as syn
+from napkon_string_matching.gpu import lib as nsmlib
+from napkon_string_matching.gpu import pack
+from napkon_string_matching.text.tokenize import gen_comp_value
+
+pytestmark = pytest.mark.gpu
+
+
+def run_gpu(engine, pl, pr, thr, **kw):
+    out = engine.all_pairs(engine.upload(pl), engine.upload(pr), thr, **kw)
+    return out, engine.last_info
+
+
+def check_against_oracle(engine, pl, pr, thr, flat=False, **kw):
+    out, info = run_gpu(engine, pl, pr, thr, flat=flat, **kw)
+    want, _ = c_oracle.all_pairs(pl, pr, thr, flat=flat)
+    assert info["count"] == len(out)
+    assert_same_triples((out["left"], out["right"], out["score"]),
+                        (want["left"], want["right"], want["score"]))
+    return out, info
+
+
+def _golden_levels(name, column):
+    meta, inputs, arrays = load_golden(name)
+    L = [gen_comp_value(v) if v is not None else None for v in inputs["left"][column]]
+    R = [gen_comp_value(v) if v is not None else None for v in inputs["right"][column]]
+    lkeep = np.array([i for i, v in enumerate(L) if v is not None])
+    rkeep = np.array([i for i, v in enumerate(R) if v is not None])
+    return meta, arrays, [L[i] for i in lkeep], [R[i] for i in rkeep], lkeep, rkeep
+
+
+@pytest.mark.parametrize("name,column", [("cfg1_400_term_jaccard", "Term"),
+                                         ("cfg2_300_tokenids_jaccard", "TokenIds"),
+                                         ("variable_80_jaccard", "Variable")])
+def test_jaccard_matches_reference_golden(engine, name, column):
+    meta, arrays, L, R, lkeep, rkeep = _golden_levels(name, column)
+    pl, pr = pack.pack_sets(L, R)
+    out, info = run_gpu(engine, pl, pr, meta["kwargs"]["score_threshold"])
+    assert info["flags"] == 0
+    assert_same_triples((lkeep[out["left"]], rkeep[out["right"]], out["score"]),
+                        (arrays["left_pos"], arrays["right_pos"], arrays["score"]))
+
+
+@pytest.mark.parametrize("name,column", [("fuzzy_150_term", "Term"),
+                                         ("fuzzy_60_question_str", "Question")])
+def test_fuzzy_matches_golden(engine, name, column):
+    meta, arrays, L, R, lkeep, rkeep = _golden_levels(name, column)
+    pl, pr = pack.pack_strings(pack.fuzzy_level_strings(L), pack.fuzzy_level_strings(R))
+    out, info = run_gpu(engine, pl, pr, meta["kwargs"]["score_threshold"])
+    assert_same_triples((lkeep[out["left"]], rkeep[out["right"]], out["score"]),
+                        (arrays["left_pos"], arrays["right_pos"], arrays["score"]))
+
+
+@pytest.mark.parametrize("thr", [0.0, 0.05, 0.3, 0.5, 0.9375, 1.5])
+def test_jaccard_thresholds_vs_oracle(engine, thr):
+    vocab = syn.vocabulary(3000)
+    fl = syn.questionnaire_frame(300, 21, vocab, "hap")
+    fr = syn.questionnaire_frame(517, 22, vocab, "pop")
+    pl, pr = pack.pack_sets([gen_comp_value(t) for t in fl["Term"]],
+                            [gen_comp_value(t) for t in fr["Term"]])
+    check_against_oracle(engine, pl, pr, thr)
+
+
+def test_jaccard_token_ids_2000_vs_oracle(engine):
+    lens, flat = syn.token_id_level_sets(2000, syn.SEED_LEFT)
+    pl = pack.pack_suffix_id_sets(lens, flat, 30000)
+    lens, flat = syn.token_id_level_sets(2000, syn.SEED_RIGHT)
+    pr = pack.pack_suffix_id_sets(lens, flat, 30000)
+    out, info = check_against_oracle(engine, pl, pr, 0.1)
+    assert info["stats"]["candidates"] >= len(out)
+    assert info["stats"]["candidates"] < info["item_pairs"]  # the filter did prune
+
+
+def test_jaccard_exact_signature_vocabulary(engine):
+    rng = np.random.default_rng(3)
+    mk = lambda n: [[[f"w{int(x)}" for x in rng.integers(0, 50, size=int(rng.integers(1, 9)))]
+                     for _ in range(int(rng.integers(1, 5)))] for _ in range(n)]
+    pl, pr = pack.pack_sets(mk(257), mk(300))
+    assert pl.sig_exact
+    out, info = check_against_oracle(engine, pl, pr, 0.2)
+    assert info["stats"]["level_merges"] == 0  # popcount path only
+
+
+def test_jaccard_flat_and_ragged_edges(engine):
+    # flat = the scalar score function on K = 1 items
+    L = [[["a", "b", "c"]], [["x"]], [["a"]], [["q", "r", "s", "t", "u"]]]
+    R = [[["b", "c", "d"]], [["x"]], [["y"]]]
+    pl, pr = pack.pack_sets(L, R)
+    out, _ = check_against_oracle(engine, pl, pr, 0.0, flat=True)
+    assert len(out) == 12
+    got = {(int(a), int(b)): s for a, b, s in zip(out["left"], out["right"], out["score"])}
+    assert got[(0, 0)] == 2 / 4 and got[(1, 1)] == 1.0 and got[(2, 2)] == 0.0
+    # unequal level counts, deep clamp, one very long set
+    big = [f"t{i}" for i in range(700)]
+    L = [[["x"], ["a"], ["a", "b"]], [["a"]], [big[:5], big[:300], big], [["p"]] * 9]
+    R = [[["y"], ["a"]], [big[100:400]], [["p"], ["p", "q"]]]
+    pl, pr = pack.pack_sets(L, R)
+    check_against_oracle(engine, pl, pr, 0.0)
+    check_against_oracle(engine, pl, pr, 0.26)
+
+
+def test_jaccard_empty_inputs_and_flags(engine):
+    pl, pr = pack.pack_sets([], [[["a"]]])
+    out, info = run_gpu(engine, pl, pr, 0.1)
+    assert len(out) == 0 and info["count"] == 0
+    pl, pr = pack.pack_sets([[["a"], []]], [[["b"], []]])
+    out, info = run_gpu(engine, pl, pr, 0.0)
+    assert info["flags"] & nsmlib.FLAG_ZERO_UNION and len(out) == 0
+    pl, pr = pack.pack_sets([[], [["a"]]], [[["a"]], []])
+    out, info = run_gpu(engine, pl, pr, 0.0)
+    assert info["flags"] & nsmlib.FLAG_EMPTY_ITEM
+    got = {(int(a), int(b)): s for a, b, s in zip(out["left"], out["right"], out["score"])}
+    assert got == {(0, 1): 0.0, (1, 0): 0.5}
+
+
+def test_jaccard_overflow_reruns_with_exact_capacity(engine):
+    lens, flat = syn.token_id_level_sets(600, 5, n_ids=200)
+    p = pack.pack_suffix_id_sets(lens, flat, 200)
+    want, _ = c_oracle.all_pairs(p, p, 0.05)
+    out = engine.all_pairs(engine.upload(p), engine.upload(p), 0.05, capacity=64)
+    assert engine.last_info["reruns"] >= 1
+    assert_same_triples((out["left"], out["right"], out["score"]),
+                        (want["left"], want["right"], want["score"]))
+
+
+def test_jaccard_row_blocks_partition_the_result(engine):
+    lens, flat = syn.token_id_level_sets(900, 8)
+    pl = pack.pack_suffix_id_sets(lens, flat, 30000)
+    dl = engine.upload(pl)
+    whole = engine.all_pairs(dl, dl, 0.2)
+    parts = [engine.all_pairs(dl, dl, 0.2, rows=(b, e)) for b, e in ((0, 123), (123, 124), (124, 900))]
+    cat = np.concatenate(parts)
+    assert_same_triples((cat["left"], cat["right"], cat["score"]),
+                        (whole["left"], whole["right"], whole["score"]))
+
+
+def test_jaccard_category_masks(engine):
+    rng = np.random.default_rng(9)
+    lens, flat = syn.token_id_level_sets(400, 31, n_ids=500)
+    p = pack.pack_suffix_id_sets(lens, flat, 500)
+    lm = rng.integers(0, 8, size=400).astype(np.uint64)
+    rm = rng.integers(0, 8, size=400).astype(np.uint64)
+    d = engine.upload(p)
+    for mode in (nsmlib.CAT_LIST_LIST, nsmlib.CAT_MEMBER):
+        out = engine.all_pairs(d, d, 0.1, l_cat=engine.upload_masks(lm),
+                               r_cat=engine.upload_masks(rm), cat_mode=mode)
+        want, _ = c_oracle.all_pairs(p, p, 0.1, l_cat=lm, r_cat=rm, cat_mode=mode)
+        assert_same_triples((out["left"], out["right"], out["score"]),
+                            (want["left"], want["right"], want["score"]))
+
+
+@pytest.mark.parametrize("thr", [0.0, 0.4, 0.7])
+def test_fuzzy_flat_strings_vs_oracle(engine, thr):
+    from napkon_string_matching.text.process import default_process
+
+    vocab = syn.vocabulary(2000)
+    sl = [[default_process(s)] for s in syn.question_strings(300, 41, vocab)]
+    sr = [[default_process(s)] for s in syn.question_strings(333, 42, vocab)]
+    sl[7], sr[11], sr[12] = [""], [""], ["a"]
+    pl, pr = pack.pack_strings(sl, sr)
+    check_against_oracle(engine, pl, pr, thr, flat=True)
+
+
+def test_fuzzy_multiword_lengths_vs_oracle(engine):
+    rng = np.random.default_rng(17)
+    alpha = list("abcdefghij klmn")
+    mk = lambda n, lo, hi: [["".join(rng.choice(alpha, size=int(rng.integers(lo, hi))))] for _ in range(n)]
+    for hi in (64, 65, 129, 200, 300, 500):
+        pl, pr = pack.pack_strings(mk(40, 1, hi), mk(70, max(1, hi - 70), hi + 1))
+        check_against_oracle(engine, pl, pr, 0.3, flat=True)
+
+
+def test_fuzzy_levels_term_shape_vs_oracle(engine):
+    vocab = syn.vocabulary(3000)
+    fl = syn.questionnaire_frame(150, 51, vocab, "hap")
+    fr = syn.questionnaire_frame(290, 52, vocab, "pop")
+    L = pack.fuzzy_level_strings([gen_comp_value(t) for t in fl["Term"]])
+    R = pack.fuzzy_level_strings([gen_comp_value(t) for t in fr["Term"]])
+    pl, pr = pack.pack_strings(L, R)
+    check_against_oracle(engine, pl, pr, 0.45)
+    check_against_oracle(engine, pl, pr, 0.0)
+
+
+def test_fuzzy_empty_items_and_flags(engine):
+    pl, pr = pack.pack_strings([[], ["abc"]], [["abc"], []])
+    out, info = run_gpu(engine, pl, pr, 0.0)
+    assert info["flags"] & nsmlib.FLAG_EMPTY_ITEM
+    got = {(int(a), int(b)): s for a, b, s in zip(out["left"], out["right"], out["score"])}
+    assert got == {(0, 1): 0.0, (1, 0): 0.5}
