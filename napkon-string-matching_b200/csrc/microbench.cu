@@ -61,7 +61,7 @@ extern "C" int nsm_microbench(int kind, uint32_t blocks, uint32_t threads, uint3
     uint64_t per_iter = 0;
     switch (kind) {
         case 0: microbench_kernel<0><<<blocks, threads, 0, stream>>>(iters, sink); per_iter = 4 * MB_CHAINS; break;
-        case 1: microbench_kernel<1><<<blocks, threads, 0, stream>>>(iters, sink); per_iter = 4 * MB_CHAINS * 2; break;
+        case 1: microbench_kernel<1><<<blocks, threads, 0, stream>>>(iters, sink); per_iter = 4 * MB_CHAINS; break;  // one IADD3 each
         case 2: microbench_kernel<2><<<blocks, threads, 0, stream>>>(iters, sink); per_iter = 4 * MB_CHAINS; break;
         // one LCS step = AND, ADD, SUB, OR on 64 bits = 8 int32 ops
         case 3: microbench_kernel<3><<<blocks, threads, 0, stream>>>(iters, sink); per_iter = 4 * (MB_CHAINS / 2) * 8; break;
