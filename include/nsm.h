@@ -61,13 +61,15 @@ typedef struct nsm_pair {
 typedef struct nsm_sets {
     const uint32_t *item_level_off; /* [n_items + 1] */
     const uint32_t *level_tok_off;  /* [n_levels + 1] */
-    const uint32_t *tok;            /* [level_tok_off[n_levels]] */
-    const uint64_t *level_sig;      /* [n_levels] 64-bit token bitset (exact iff sig_exact) */
-    const uint32_t *level_info;     /* [n_levels] size | min(size - popc(sig), 255) << 16 */
+    const uint32_t *tok;            /* [level_tok_off[n_levels]] ids ranked by falling frequency */
+    const uint64_t *level_head;     /* [n_levels] exact bitset of the level's ids 0..63 */
+    const uint64_t *level_tail;     /* [n_levels] signature of its ids >= 64 (exact iff exact_bits) */
+    const uint32_t *level_info;     /* [n_levels] size | min(n_tail - popc(tail), 255) << 16 | n_head << 24 */
+    const uint64_t *item_any;       /* [n_items][2] OR of (head, tail) over the levels compare_terms uses */
     uint32_t n_items;
     uint32_t n_levels;
     uint32_t max_levels; /* max levels of any item on this side */
-    uint32_t sig_exact;  /* 1: vocabulary <= 64 ids, bit == id, popc(sig & sig) is the intersection */
+    uint32_t exact_bits; /* 1: vocabulary <= 128 ids, tail bit == id - 64, no token merge needed */
 } nsm_sets_t;
 
 /* One cohort side for fuzzy_match: per level the processed string QRatio sees
@@ -100,9 +102,10 @@ typedef struct nsm_job {
     uint64_t *out_stats; /* optional [NSM_N_STATS] counters, may be NULL */
 } nsm_job_t;
 
-#define NSM_STAT_CANDIDATES 0 /* item pairs that reached exact scoring */
-#define NSM_STAT_LEVEL_EVALS 1 /* score_func evaluations done exactly (merge / LCS) */
+#define NSM_STAT_CANDIDATES 0   /* item pairs that reached exact float64 scoring */
+#define NSM_STAT_LEVEL_EVALS 1  /* score_func evaluations done exactly (popcount / merge / LCS) */
 #define NSM_STAT_LEVEL_MERGES 2 /* of those, ones that needed a token merge */
+#define NSM_STAT_BOUND_PAIRS 3  /* item pairs that reached the per-level bound (shared a signature bit) */
 #define NSM_N_STATS 4
 
 int nsm_version(void);

@@ -41,7 +41,7 @@ class DeviceCohort:
 
 
 class Engine:
-    def __init__(self, device: Optional[int] = None, max_pairs_per_block: int = 1 << 26):
+    def __init__(self, device: Optional[int] = None, max_pairs_per_block: int = 1 << 30):
         _require_cuda()
         self.lib = nsmlib.load()
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
@@ -66,8 +66,7 @@ class Engine:
     @staticmethod
     def _arrays(packed) -> List[np.ndarray]:
         if isinstance(packed, PackedSets):
-            return [packed.item_level_off, packed.level_tok_off, packed.tok, packed.level_sig,
-                    packed.level_info]
+            return packed.arrays()
         if isinstance(packed, PackedStrings):
             return [packed.item_level_off, packed.level_chr_off, packed.chr]
         raise TypeError(type(packed))
@@ -87,7 +86,7 @@ class Engine:
         tensors = [self._to_device(a) for a in (pinned if pinned is not None else arrays)]
         if isinstance(packed, PackedSets):
             st = nsmlib.NsmSets(*[t.data_ptr() for t in tensors], packed.n_items, packed.n_levels,
-                                packed.max_levels, int(packed.sig_exact))
+                                packed.max_levels, int(packed.exact_bits))
             per_level = packed.level_sizes()
             kind = "sets"
         else:
@@ -182,7 +181,8 @@ class Engine:
         host_fill = 0
         if capacity is None:
             have = self._buffers["out"].numel() // 16 if "out" in self._buffers else 0
-            capacity = max(have, min(self.max_pairs_per_block, max(1 << 16, info["item_pairs"] // 8)))
+            capacity = max(have, min(self.max_pairs_per_block, 1 << 24,
+                                     max(1 << 16, info["item_pairs"] // 8)))
         while blocks:
             rb, re_ = blocks.pop(0)
             count, flags, stats = run(rb, re_, capacity)

@@ -14,7 +14,7 @@ NSM_OK = 0
 FLAG_OVERFLOW, FLAG_ZERO_UNION, FLAG_EMPTY_ITEM = 1, 2, 4
 CAT_OFF, CAT_LIST_LIST, CAT_MEMBER = 0, 1, 2
 N_STATS = 4
-STAT_NAMES = ("candidates", "level_evals", "level_merges", "reserved")
+STAT_NAMES = ("candidates", "level_evals", "level_merges", "bound_pairs")
 
 PAIR_DTYPE = np.dtype([("left", np.uint32), ("right", np.uint32), ("score", np.float64)])
 assert PAIR_DTYPE.itemsize == 16
@@ -25,9 +25,10 @@ EXPORTS = ("nsm_version", "nsm_last_error", "nsm_jaccard_allpairs", "nsm_qratio_
 
 class NsmSets(C.Structure):
     _fields_ = [("item_level_off", C.c_void_p), ("level_tok_off", C.c_void_p),
-                ("tok", C.c_void_p), ("level_sig", C.c_void_p), ("level_info", C.c_void_p),
+                ("tok", C.c_void_p), ("level_head", C.c_void_p), ("level_tail", C.c_void_p),
+                ("level_info", C.c_void_p), ("item_any", C.c_void_p),
                 ("n_items", C.c_uint32), ("n_levels", C.c_uint32), ("max_levels", C.c_uint32),
-                ("sig_exact", C.c_uint32)]
+                ("exact_bits", C.c_uint32)]
 
 
 class NsmStrings(C.Structure):

@@ -7,9 +7,16 @@ Jaccard operands (``PackedSets``) — one cohort side, CSR over items -> levels 
     item_level_off  uint32[n_items+1]   levels of item i are item_level_off[i]:item_level_off[i+1]
     level_tok_off   uint32[n_levels+1]  tokens of level g are tok[level_tok_off[g]:level_tok_off[g+1]]
     tok             uint32[n_tok]       token ids, sorted and unique inside a level
-    level_sig       uint64[n_levels]    64-bit token bitset of the level (bit = id if the whole
-                                        vocabulary has <= 64 ids, else a multiplicative hash of id)
-    level_info      uint32[n_levels]    size | min(size - popcount(sig), 255) << 16
+    level_head      uint64[n_levels]    exact bitset of the level's ids 0..63
+    level_tail      uint64[n_levels]    signature of the ids >= 64 (bit = id - 64 if the whole
+                                        vocabulary has <= 128 ids, else a multiplicative hash)
+    level_info      uint32[n_levels]    size | min(n_tail - popcount(tail), 255) << 16 | n_head << 24
+    item_any        uint64[n_items, 2]  OR of (head, tail) over the levels compare_terms can use
+                                        (levels 1..K-1, or level 0 when K == 1)
+
+Token ids are assigned in order of falling frequency over all packed sides, so ids 0..63 (the
+"head") are the 64 most frequent tokens: under the Zipf-like token statistics of questionnaire
+text and MeSH ids most shared tokens are head tokens and their intersection is one popcount.
 
 Levels are what ``ComparableData.gen_comp_value`` returns for an item
 (/root/reference/napkon_string_matching/types/comparable_data.py:283-285): level j is the token
@@ -47,10 +54,12 @@ class PackedSets:
     item_level_off: np.ndarray
     level_tok_off: np.ndarray
     tok: np.ndarray
-    level_sig: np.ndarray
+    level_head: np.ndarray
+    level_tail: np.ndarray
     level_info: np.ndarray
+    item_any: np.ndarray
     n_vocab: int
-    sig_exact: bool
+    exact_bits: bool
     max_levels: int = 0
 
     @property
@@ -61,6 +70,10 @@ class PackedSets:
     def n_levels(self) -> int:
         return len(self.level_tok_off) - 1
 
+    def arrays(self):
+        return [self.item_level_off, self.level_tok_off, self.tok, self.level_head,
+                self.level_tail, self.level_info, self.item_any]
+
     def level_sizes(self) -> np.ndarray:
         return np.diff(self.level_tok_off.astype(np.int64))
 
@@ -68,8 +81,7 @@ class PackedSets:
         return np.diff(self.item_level_off.astype(np.int64))
 
     def nbytes(self) -> int:
-        return sum(a.nbytes for a in (self.item_level_off, self.level_tok_off, self.tok,
-                                      self.level_sig, self.level_info))
+        return sum(a.nbytes for a in self.arrays())
 
     def rows(self, begin: int, end: int) -> "PackedSets":
         """Items begin:end as an independent pack (used by tests and CPU baselines)."""
@@ -78,8 +90,9 @@ class PackedSets:
         return PackedSets(
             (self.item_level_off[begin : end + 1] - np.uint32(g0)).astype(np.uint32),
             (self.level_tok_off[g0 : g1 + 1] - np.uint32(t0)).astype(np.uint32),
-            self.tok[t0:t1].copy(), self.level_sig[g0:g1].copy(), self.level_info[g0:g1].copy(),
-            self.n_vocab, self.sig_exact, self.max_levels)
+            self.tok[t0:t1].copy(), self.level_head[g0:g1].copy(), self.level_tail[g0:g1].copy(),
+            self.level_info[g0:g1].copy(), self.item_any[begin:end].copy(), self.n_vocab,
+            self.exact_bits, self.max_levels)
 
 
 @dataclass
@@ -120,11 +133,14 @@ class PackedStrings:
 # ------------------------------------------------------------------------------------------
 # signatures
 # ------------------------------------------------------------------------------------------
-def signature_bits(ids: np.ndarray, sig_exact: bool) -> np.ndarray:
-    """Bit position (0..63) of every token id."""
+HEAD_IDS = 64
+
+
+def tail_bits(ids: np.ndarray, exact_bits: bool) -> np.ndarray:
+    """Bit position (0..63) in the tail signature of every token id >= 64."""
     ids = ids.astype(np.uint32, copy=False)
-    if sig_exact:
-        return ids.astype(np.uint64)
+    if exact_bits:
+        return (ids - np.uint32(HEAD_IDS)).astype(np.uint64)
     with np.errstate(over="ignore"):
         return ((ids * SIG_HASH_MULT) >> np.uint32(26)).astype(np.uint64)
 
@@ -141,21 +157,52 @@ def _segment_or(values: np.ndarray, offsets: np.ndarray) -> np.ndarray:
 
 
 def finish_sets(item_level_off, level_tok_off, tok, n_vocab: int) -> PackedSets:
-    """Adds signatures / info words to a CSR whose levels are already sorted and unique."""
+    """Adds signatures / info words to a CSR whose levels are already sorted and unique and
+    whose ids are frequency-ranked."""
     item_level_off = np.ascontiguousarray(item_level_off, dtype=np.uint32)
     level_tok_off = np.ascontiguousarray(level_tok_off, dtype=np.uint32)
     tok = np.ascontiguousarray(tok, dtype=np.uint32)
     sizes = np.diff(level_tok_off.astype(np.int64))
     if len(sizes) and sizes.max() > MAX_LEVEL_SIZE:
         raise PackError(f"a level holds {sizes.max()} tokens; the packed format allows 65535")
-    sig_exact = n_vocab <= 64
-    bits = np.left_shift(np.uint64(1), signature_bits(tok, sig_exact))
-    sig = _segment_or(bits, level_tok_off)
-    extra = np.minimum(sizes - np.bitwise_count(sig).astype(np.int64), 255)
-    info = (sizes.astype(np.uint32)) | (extra.astype(np.uint32) << np.uint32(16))
+    exact_bits = n_vocab <= 2 * HEAD_IDS
+    is_head = tok < HEAD_IDS
+    one = np.uint64(1)
+    head_bit = np.where(is_head, np.left_shift(one, np.where(is_head, tok, 0).astype(np.uint64)),
+                        np.uint64(0))
+    tail_bit = np.where(is_head, np.uint64(0),
+                        np.left_shift(one, tail_bits(np.where(is_head, HEAD_IDS, tok), exact_bits)))
+    head = _segment_or(head_bit, level_tok_off)
+    tail = _segment_or(tail_bit, level_tok_off)
+    n_head = np.bitwise_count(head).astype(np.int64)
+    extra = np.minimum(sizes - n_head - np.bitwise_count(tail).astype(np.int64), 255)
+    info = sizes.astype(np.uint32) | (extra.astype(np.uint32) << np.uint32(16)) \
+        | (n_head.astype(np.uint32) << np.uint32(24))
     k = np.diff(item_level_off.astype(np.int64))
-    return PackedSets(item_level_off, level_tok_off, tok, sig, info.astype(np.uint32),
-                      int(n_vocab), bool(sig_exact), int(k.max()) if len(k) else 0)
+    # union over the levels compare_terms can touch: 1..K-1, or 0 when K == 1
+    n_items, n_levels = len(k), len(sizes)
+    item_any = np.zeros((n_items, 2), dtype=np.uint64)
+    if n_levels:
+        level_item = np.repeat(np.arange(n_items, dtype=np.int64), k)
+        level_j = np.arange(n_levels, dtype=np.int64) - item_level_off[:-1].astype(np.int64)[level_item]
+        used = (level_j >= 1) | (k[level_item] == 1)
+        np.bitwise_or.at(item_any[:, 0], level_item[used], head[used])
+        np.bitwise_or.at(item_any[:, 1], level_item[used], tail[used])
+    return PackedSets(item_level_off, level_tok_off, tok, head, tail, info.astype(np.uint32),
+                      item_any, int(n_vocab), bool(exact_bits), int(k.max()) if len(k) else 0)
+
+
+def rank_by_frequency(codes_per_side: List[np.ndarray], n_vocab: int) -> List[np.ndarray]:
+    """Renumbers ids so that id 0 is the most frequent token over all sides."""
+    if n_vocab == 0:
+        return codes_per_side
+    counts = np.zeros(n_vocab, dtype=np.int64)
+    for c in codes_per_side:
+        counts += np.bincount(c, minlength=n_vocab)
+    order = np.argsort(-counts, kind="stable")
+    rank = np.empty(n_vocab, dtype=np.int64)
+    rank[order] = np.arange(n_vocab, dtype=np.int64)
+    return [rank[c] for c in codes_per_side]
 
 
 def _csr_from_nested(items_levels: Sequence[Sequence[Sequence]]) -> Tuple[np.ndarray, np.ndarray, list]:
@@ -201,20 +248,39 @@ def pack_sets(*sides: Sequence[Sequence[Sequence[str]]]) -> List[PackedSets]:
         n_vocab = len(uniques)
     else:
         codes_all, n_vocab = np.zeros(0, dtype=np.int64), 0
-    out, pos = [], 0
-    for item_level_off, level_off, flat in parts:
+    sides_codes, pos = [], 0
+    for _, level_off, flat in parts:
         codes = codes_all[pos : pos + len(flat)].astype(np.int64)
         pos += len(flat)
-        new_off, codes = _sort_unique_levels(level_off, codes)
+        sides_codes.append(_sort_unique_levels(level_off, codes))
+    ranked = rank_by_frequency([c for _, c in sides_codes], n_vocab)
+    out = []
+    for (item_level_off, _, _), (new_off, _), codes in zip(parts, sides_codes, ranked):
+        new_off, codes = _sort_unique_levels(new_off, codes)  # ids changed: sort again
         out.append(finish_sets(item_level_off, new_off, codes, n_vocab))
     return out
 
 
-def pack_suffix_id_sets(lens: np.ndarray, flat_ids: np.ndarray, n_vocab: int) -> PackedSets:
+def frequency_rank(id_arrays: Sequence[np.ndarray], n_vocab: int) -> np.ndarray:
+    """rank[id] = position of ``id`` when ids are ordered by falling count over all arrays."""
+    counts = np.zeros(n_vocab, dtype=np.int64)
+    for a in id_arrays:
+        counts += np.bincount(np.asarray(a, dtype=np.int64), minlength=n_vocab)
+    order = np.argsort(-counts, kind="stable")
+    rank = np.empty(n_vocab, dtype=np.int64)
+    rank[order] = np.arange(n_vocab, dtype=np.int64)
+    return rank
+
+
+def pack_suffix_id_sets(lens: np.ndarray, flat_ids: np.ndarray, n_vocab: int,
+                        rank: np.ndarray | None = None) -> PackedSets:
     """Integer fast path for list-valued columns whose parts are single tokens (``TokenIds``):
     item i has the id list ``v = flat_ids[o_i : o_i + lens[i]]`` and level j is ``set(v[-(j+1):])``
-    (Q2), built without Python loops."""
+    (Q2), built without Python loops.  ``rank`` (see :func:`frequency_rank`) renumbers the ids;
+    all sides of one comparison must be packed with the same ``rank``."""
     lens = np.asarray(lens, dtype=np.int64)
+    if rank is not None:
+        flat_ids = np.asarray(rank)[np.asarray(flat_ids, dtype=np.int64)]
     n = len(lens)
     item_end = np.cumsum(lens)
     item_level_off = np.zeros(n + 1, dtype=np.int64)

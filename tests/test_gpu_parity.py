@@ -80,10 +80,10 @@ def test_jaccard_token_ids_2000_vs_oracle(engine):
 
 def test_jaccard_exact_signature_vocabulary(engine):
     rng = np.random.default_rng(3)
-    mk = lambda n: [[[f"w{int(x)}" for x in rng.integers(0, 50, size=int(rng.integers(1, 9)))]
+    mk = lambda n: [[[f"w{int(x)}" for x in rng.integers(0, 120, size=int(rng.integers(1, 9)))]
                      for _ in range(int(rng.integers(1, 5)))] for _ in range(n)]
     pl, pr = pack.pack_sets(mk(257), mk(300))
-    assert pl.sig_exact
+    assert pl.exact_bits
     out, info = check_against_oracle(engine, pl, pr, 0.2)
     assert info["stats"]["level_merges"] == 0  # popcount path only
 

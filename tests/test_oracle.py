@@ -125,27 +125,44 @@ def test_pack_sets_layout_and_signatures():
     assert list(pl.item_level_off) == [0, 2, 2, 3]
     assert list(pl.level_sizes()) == [2, 3, 1]
     assert pr.n_levels == 2 and list(pr.level_sizes()) == [1, 0]
-    assert pl.sig_exact and pl.n_vocab == 4
+    assert pl.exact_bits and pl.n_vocab == 4
     for p in (pl, pr):
         for g in range(p.n_levels):
             toks = p.tok[p.level_tok_off[g]:p.level_tok_off[g + 1]]
             assert list(toks) == sorted(set(toks))
-            assert int(p.level_sig[g]) == sum(1 << int(t) for t in toks)
-            assert p.level_info[g] & 0xFFFF == len(toks) and p.level_info[g] >> 16 == 0
+            assert int(p.level_head[g]) == sum(1 << int(t) for t in toks) and p.level_tail[g] == 0
+            assert p.level_info[g] & 0xFFFF == len(toks) and p.level_info[g] >> 24 == len(toks)
+    # ids are ranked by frequency over both sides: "a" (3 uses incl. duplicates) gets id 0
+    assert pl.tok[pl.level_tok_off[0]] == 0
+    # item_any = OR over the levels compare_terms can use (1..K-1, or 0 when K == 1)
+    assert int(pl.item_any[0, 0]) == int(pl.level_head[1]) and int(pl.item_any[1, 0]) == 0
+    assert int(pl.item_any[2, 0]) == int(pl.level_head[2])
+    assert int(pr.item_any[0, 0]) == 0  # K == 2: only level 1, which is empty
 
 
 def test_pack_hashed_signature_invariants():
     rng = np.random.default_rng(5)
-    items = [[[f"t{int(x)}" for x in rng.integers(0, 5000, size=int(rng.integers(0, 40)))]
-              for _ in range(int(rng.integers(1, 5)))] for _ in range(200)]
+    items = [[[f"t{int(x)}" for x in rng.zipf(1.2, size=int(rng.integers(0, 40)))]
+              for _ in range(int(rng.integers(1, 5)))] for _ in range(300)]
     (p,) = pack.pack_sets(items)
-    assert not p.sig_exact
+    assert not p.exact_bits and p.n_vocab > 128
     sizes = p.level_sizes()
-    bits = np.bitwise_count(p.level_sig)
-    assert np.all(bits <= sizes)
-    assert np.array_equal((p.level_info >> 16) & 0xFF, np.minimum(sizes - bits, 255))
+    n_head, n_tail_bits = np.bitwise_count(p.level_head), np.bitwise_count(p.level_tail)
+    assert np.array_equal(p.level_info >> 24, n_head)
+    assert np.array_equal((p.level_info >> 16) & 0xFF, np.minimum(sizes - n_head - n_tail_bits, 255))
     assert np.array_equal(p.level_info & 0xFFFF, sizes)
-    assert np.all((sizes == 0) == (p.level_sig == 0))
+    for g in range(p.n_levels):
+        toks = p.tok[p.level_tok_off[g]:p.level_tok_off[g + 1]]
+        assert int(p.level_head[g]) == sum(1 << int(t) for t in toks if t < 64)
+        assert (p.level_tail[g] == 0) == (not any(t >= 64 for t in toks))
+    # head ids are the most frequent ones
+    counts = np.bincount(p.tok, minlength=p.n_vocab)
+    assert counts[:64].min() >= counts[64:].max()
+    k = p.levels_per_item()
+    for i in np.nonzero(k >= 2)[0][:50]:
+        g0 = int(p.item_level_off[i])
+        want = np.bitwise_or.reduce(p.level_head[g0 + 1:g0 + k[i]])
+        assert int(p.item_any[i, 0]) == int(want)
 
 
 def test_pack_suffix_id_sets_equals_generic_packer():
