@@ -15,8 +15,14 @@ def gen_hash(string: str) -> str:
 
 
 def _column_property(column: str) -> property:
-    return property(lambda self: self._data[column],
-                    lambda self, value: self._data.__setitem__(column, value))
+    def fget(self):
+        return self._data[column]
+
+    def fset(self, value):
+        frame = self._data
+        frame[column] = value
+
+    return property(fget, fset)
 
 
 class Data:

@@ -49,3 +49,58 @@ def engine():
     from napkon_string_matching.gpu.engine import Engine
 
     return Engine()
+
+
+class OracleEngine:
+    """Test double for gpu.engine.Engine in the CPU suite: same surface, but pairs are scored by
+    the C oracle.  It lets the host logic around the kernels (filters, exceptions, frames,
+    sharding) be tested without a GPU.  Never used by the product."""
+
+    def __init__(self):
+        self.last_info = {}
+        self.launches = 0
+
+    class _Cohort:
+        def __init__(self, packed):
+            import numpy as _np
+
+            self.packed = packed
+            self.kind = "sets" if hasattr(packed, "tok") else "strings"
+            self.n_items = packed.n_items
+            self.weights = _np.ones(packed.n_items)
+
+    def upload(self, packed, pinned=None):
+        return self._Cohort(packed)
+
+    def upload_masks(self, masks):
+        return masks
+
+    def all_pairs(self, left, right, threshold, *, flat=False, rows=None, l_cat=None, r_cat=None,
+                  cat_mode=0, **_):
+        from oracle import c_oracle
+        from napkon_string_matching.gpu.lib import PAIR_DTYPE
+
+        begin, end = rows if rows is not None else (0, left.n_items)
+        out, flags = c_oracle.all_pairs(left.packed, right.packed, threshold, flat=flat,
+                                        l_begin=begin, l_end=end, l_cat=l_cat, r_cat=r_cat,
+                                        cat_mode=cat_mode)
+        self.last_info = {"count": len(out), "flags": flags}
+        return out.astype(PAIR_DTYPE)
+
+
+@pytest.fixture
+def oracle_engine(monkeypatch):
+    """Routes the host API through OracleEngine for the duration of one CPU test."""
+    import napkon_string_matching.gpu.engine as eng_mod
+
+    double = OracleEngine()
+    monkeypatch.setattr(eng_mod, "default_engine", lambda: double)
+    return double
+
+
+@pytest.fixture
+def cuda_engine(monkeypatch, engine):
+    import napkon_string_matching.gpu.engine as eng_mod
+
+    monkeypatch.setattr(eng_mod, "default_engine", lambda: engine)
+    return engine
