@@ -64,12 +64,19 @@ typedef struct nsm_sets {
     const uint32_t *tok;            /* [level_tok_off[n_levels]] ids ranked by falling frequency */
     const uint64_t *level_head;     /* [n_levels] exact bitset of the level's ids 0..63 */
     const uint64_t *level_tail;     /* [n_levels] signature of its ids >= 64 (exact iff exact_bits) */
+    const uint64_t *level_tail2;    /* [n_levels] second, independent signature of the ids >= 64 */
     const uint32_t *level_info;     /* [n_levels] size | min(n_tail - popc(tail), 255) << 16 | n_head << 24 */
     const uint64_t *item_any;       /* [n_items][2] OR of (head, tail) over the levels compare_terms uses */
+    const uint32_t *item_k;         /* [n_items] number of levels */
+    const uint64_t *slot_head;      /* [n_slots][n_items] level_head of level min(t, K-1), slot t-1 */
+    const uint64_t *slot_tail;      /* [n_slots][n_items] */
+    const uint32_t *slot_info;      /* [n_slots][n_items] */
     uint32_t n_items;
     uint32_t n_levels;
     uint32_t max_levels; /* max levels of any item on this side */
+    uint32_t n_slots;    /* clamp(max_levels - 1, 1, 10) */
     uint32_t exact_bits; /* 1: vocabulary <= 128 ids, tail bit == id - 64, no token merge needed */
+    uint32_t reserved_;
 } nsm_sets_t;
 
 /* One cohort side for fuzzy_match: per level the processed string QRatio sees

@@ -4,26 +4,28 @@
 // "intersection_vs_union" (/root/reference/napkon_string_matching/types/comparable_data.py:223-243,
 // compare_terms :248-265, compare/score_functions.py:6-13).
 //
-// Data: every level set carries a 128-bit summary (pack.py): `head` = exact bitset of its 64 most
-// frequent vocabulary ids, `tail` = signature of the rest, plus sizes.  Every item carries the OR
-// of those over the levels compare_terms can touch (`item_any`).
+// Data (pack.py): every level set carries a summary: `head` = exact bitset of its 64 most
+// frequent vocabulary ids, `tail` = 64-bit signature of the rest, and its sizes.  The summaries
+// are also laid out by compare_terms' step ("slot" t-1 holds level min(t, K-1) of each item),
+// slot-major, so that the data of a block of consecutive items is contiguous per step.
 //
-// Work decomposition: a unit is one block of JT_THREADS right items x a group of left tiles
-// (<= JT_LEFT items each).  The right block is staged once per unit in shared memory, slot-major
-// (slot t = the level compare_terms uses at step t, i.e. min(t, K-1)) so that lane i reads word i:
-// conflict-free.  The left tile is staged as CSR and read by broadcast.  Each warp then runs a
-// three-stage funnel over its 32 right items x the tile's left items, re-compacting the survivors
-// of every stage through a per-warp shared-memory queue (ballot + popc) so that each stage runs
-// with 32 busy lanes:
-//   A  ANY      (per item pair, ~6 integer ops) item_any(left) & item_any(right) == 0 proves that
-//               no level pair shares a token: score 0, below any positive threshold.
-//   B  BOUND    (per level, integer + fp32 with round-up) exact head intersection by popcount plus
-//               an upper bound of the tail intersection from the signatures gives an upper bound
-//               of every level score; the compare_terms weights are accumulated with directed
-//               rounding, stopping when bound + remaining weight cannot reach the threshold.
-//   C  EXACT    per used level the exact |A & B| (popcount; a merge over the tail ids only when
-//               the tail signatures collide), the reference's int/int float64 division and its
-//               accumulation order; score >= threshold in float64.
+// Work decomposition: a unit is one block of JT_THREADS right items x a group of left tiles of
+// JT_LEFT items.  The right block's slots are staged once per unit in shared memory, one column
+// per thread (lane i reads word i: conflict-free); the left tile's slots likewise.  Each warp
+// runs a three-stage funnel over its 32 right items x the tile's left items, re-compacting the
+// survivors of every stage through a per-warp shared-memory queue (ballot + popc) so that each
+// stage runs with 32 busy lanes:
+//   A  ANY     (per item pair, ~8 integer ops) the OR of the summaries over the first D steps
+//              (2^-D < threshold: later steps cannot lift a zero score over the threshold) shares
+//              no bit => no level pair that matters shares a token => pair proven < threshold.
+//   B  BOUND   (per step, integer + fp32 round-up) exact head intersection by popcount plus an
+//              upper bound of the tail intersection from the signatures bounds every level score;
+//              compare_terms' weights are accumulated with directed rounding.  The first four
+//              steps run as straight-line code, the rest in a loop that stops as soon as
+//              bound + remaining weight cannot reach the threshold.
+//   C  EXACT   per used level the exact |A & B| (popcount; only if both tail signatures collide,
+//              a merge over the tail ids), the reference's int/int float64 division and its
+//              accumulation order; score >= threshold in float64.
 // Kept pairs go to a per-warp staging buffer and are flushed with one global atomic per ~100
 // records as coalesced 16-byte stores.
 #include "nsm_common.cuh"
@@ -31,36 +33,32 @@
 namespace nsm {
 
 constexpr int JT_THREADS = 256;  // right items per block (= threads per CTA)
-constexpr int JT_LEFT = 64;      // left items per tile (upper bound)
-constexpr int J_LCAP = 1024;     // left levels staged per tile (upper bound)
-constexpr int J_RSLOTS = 10;     // right slots staged per item; deeper steps gather from global
+constexpr int JT_LEFT = 64;      // left items per tile
+constexpr int J_SLOTS = 10;      // steps staged per item (pack.py SLOT_CAP)
 constexpr int J_GROUP = 8;       // left tiles per unit
 constexpr int J_RCP = 512;       // reciprocal table size
 constexpr int J_WARPS = JT_THREADS / 32;
 constexpr int J_OUT = 128;       // staged output records per warp
+constexpr int J_UNROLL = 4;      // steps of stage B that run as straight-line code
 
 struct JaccardParams {
     nsm_sets_t L, R;
     nsm_job_t job;
     float thr_lo;        // filter threshold (see filter_threshold); -inf: everything passes
-    uint32_t tile_left;  // left items per tile, tile_left * L.max_levels <= J_LCAP
+    uint32_t any_depth;  // D of stage A; 0: use the packed all-level item_any
     uint32_t n_ltiles, n_lgroups, n_rblocks;
 };
 
 struct __align__(16) JaccardSmem {
-    // left tile, CSR
-    uint64_t l_head[J_LCAP];
-    uint64_t l_tail[J_LCAP];
-    uint32_t l_info[J_LCAP];
-    uint32_t l_tok_off[J_LCAP + 1];
-    uint32_t l_g0[JT_LEFT + 1];  // tile-relative first level of each left item
+    uint64_t l_head[J_SLOTS][JT_LEFT];
+    uint64_t l_tail[J_SLOTS][JT_LEFT];
+    uint32_t l_info[J_SLOTS][JT_LEFT];
+    uint32_t l_k[JT_LEFT];
     ulonglong2 l_any[JT_LEFT];
     uint64_t l_cat[JT_LEFT];
-    // right block, slot-major
-    uint64_t r_head[J_RSLOTS][JT_THREADS];
-    uint64_t r_tail[J_RSLOTS][JT_THREADS];
-    uint32_t r_info[J_RSLOTS][JT_THREADS];
-    uint32_t r_g0[JT_THREADS];
+    uint64_t r_head[J_SLOTS][JT_THREADS];
+    uint64_t r_tail[J_SLOTS][JT_THREADS];
+    uint32_t r_info[J_SLOTS][JT_THREADS];
     uint32_t r_k[JT_THREADS];
     float rcp_up[J_RCP];
     uint32_t qa[J_WARPS][64];
@@ -99,6 +97,22 @@ struct LevelWords {
     uint32_t info;
 };
 
+// upper bound of |A & B| of one level pair from the summaries (exact when the tails share no bit)
+__device__ __forceinline__ uint32_t bound_intersection(const LevelWords &A, const LevelWords &B,
+                                                       bool exact_bits) {
+    uint32_t ih = __popcll(A.head & B.head);
+    const uint64_t tb = A.tail & B.tail;
+    if (tb) {
+        // shared tail bits + the ids either side folded onto an occupied bit bound the shared
+        // tail ids (255 = saturated fold count)
+        const uint32_t ex = min((A.info >> 16) & 0xffu, (B.info >> 16) & 0xffu);
+        uint32_t it = exact_bits ? __popcll(tb) : (ex == 255u ? 0xffffu : __popcll(tb) + ex);
+        it = min(it, min((A.info & 0xffffu) - (A.info >> 24), (B.info & 0xffffu) - (B.info >> 24)));
+        ih += it;
+    }
+    return ih;
+}
+
 __global__ void __launch_bounds__(JT_THREADS, 2)
 jaccard_allpairs_kernel(const JaccardParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -110,6 +124,9 @@ jaccard_allpairs_kernel(const JaccardParams p) {
     const bool exact_bits = p.L.exact_bits != 0 && p.R.exact_bits != 0;
     const double thr = p.job.threshold;
     const bool pass_all = !(p.thr_lo > -INFINITY) && !(p.thr_lo != p.thr_lo);  // thr <= 0
+    const uint32_t SL = p.L.n_slots, SR = p.R.n_slots;
+    // an item whose levels do not all fit its side's slots needs the CSR arrays for deep steps
+    const bool l_deep = p.L.max_levels > SL + 1, r_deep = p.R.max_levels > SR + 1;
 
     for (unsigned u = tid; u < J_RCP; u += JT_THREADS) s.rcp_up[u] = u ? __frcp_ru((float)u) : 0.0f;
     if (tid < NSM_N_STATS) s.stats[tid] = 0;
@@ -150,48 +167,62 @@ jaccard_allpairs_kernel(const JaccardParams p) {
     const uint32_t n_units = p.n_lgroups * p.n_rblocks;
     for (uint32_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         const uint32_t rb = unit / p.n_lgroups, lgroup = unit - rb * p.n_lgroups;
+        const uint32_t r0 = rb * JT_THREADS;
 
         __syncthreads();  // previous unit fully consumed
-        // ---- stage my right item, slot-major --------------------------------------------
-        const uint32_t r = rb * JT_THREADS + tid;
+        // ---- stage my right item's slots: one column per thread ---------------------------
+        const uint32_t r = r0 + tid;
         const bool r_valid = r < p.R.n_items;
-        uint32_t rg0 = 0, kr = 0;
+        uint32_t kr = 0;
         uint64_t rcat = 0, rany_h = 0, rany_t = 0;
         if (r_valid) {
-            rg0 = __ldg(p.R.item_level_off + r);
-            kr = __ldg(p.R.item_level_off + r + 1) - rg0;
+            kr = __ldg(p.R.item_k + r);
             if (p.job.cat_mode) rcat = __ldg(p.job.r_cat + r);
+        }
+        s.r_k[tid] = kr;
+#pragma unroll
+        for (int sl = 0; sl < J_SLOTS; ++sl) {
+            if ((uint32_t)sl < SR) {
+                uint64_t h = 0, t = 0;
+                uint32_t inf = 0;
+                if (r_valid) {
+                    const size_t at = (size_t)sl * p.R.n_items + r;
+                    h = __ldg(p.R.slot_head + at);
+                    t = __ldg(p.R.slot_tail + at);
+                    inf = __ldg(p.R.slot_info + at);
+                }
+                s.r_head[sl][tid] = h;
+                s.r_tail[sl][tid] = t;
+                s.r_info[sl][tid] = inf;
+                if ((uint32_t)sl < p.any_depth) { rany_h |= h; rany_t |= t; }
+            }
+        }
+        if (p.any_depth == 0 && r_valid) {
             const ulonglong2 any = __ldg(reinterpret_cast<const ulonglong2 *>(p.R.item_any) + r);
             rany_h = any.x; rany_t = any.y;
         }
-        s.r_g0[tid] = rg0;
-        s.r_k[tid] = kr;
-#pragma unroll
-        for (int sl = 0; sl < J_RSLOTS; ++sl) {
-            uint64_t h = 0, t = 0;
-            uint32_t inf = 0;
-            if (kr) {
-                const uint32_t g = rg0 + (flat ? 0u : min((uint32_t)sl + 1u, kr - 1));
-                h = __ldg(p.R.level_head + g);
-                t = __ldg(p.R.level_tail + g);
-                inf = __ldg(p.R.level_info + g);
-            }
-            s.r_head[sl][tid] = h;
-            s.r_tail[sl][tid] = t;
-            s.r_info[sl][tid] = inf;
-        }
 
-        // level words of the right item in column `rc` at step t
-        auto right_level = [&](uint32_t rc, uint32_t t, uint32_t c_rg0, uint32_t c_kr) {
+        // summary words of one item at step t (t >= 1); col = column in the staged block
+        auto left_level = [&](uint32_t li, uint32_t item, uint32_t t, uint32_t k) {
             LevelWords w;
-            if (t <= (uint32_t)J_RSLOTS) {
-                w.head = s.r_head[t - 1][rc];
-                w.tail = s.r_tail[t - 1][rc];
-                w.info = s.r_info[t - 1][rc];
+            if (!l_deep || t <= SL || k <= SL + 1) {
+                const uint32_t sl = min(t, SL) - 1;
+                w.head = s.l_head[sl][li]; w.tail = s.l_tail[sl][li]; w.info = s.l_info[sl][li];
             } else {
-                const uint32_t g = c_rg0 + min(t, c_kr - 1);
-                w.head = __ldg(p.R.level_head + g);
-                w.tail = __ldg(p.R.level_tail + g);
+                const uint32_t g = __ldg(p.L.item_level_off + item) + min(t, k - 1);
+                w.head = __ldg(p.L.level_head + g); w.tail = __ldg(p.L.level_tail + g);
+                w.info = __ldg(p.L.level_info + g);
+            }
+            return w;
+        };
+        auto right_level = [&](uint32_t rc, uint32_t item, uint32_t t, uint32_t k) {
+            LevelWords w;
+            if (!r_deep || t <= SR || k <= SR + 1) {
+                const uint32_t sl = min(t, SR) - 1;
+                w.head = s.r_head[sl][rc]; w.tail = s.r_tail[sl][rc]; w.info = s.r_info[sl][rc];
+            } else {
+                const uint32_t g = __ldg(p.R.item_level_off + item) + min(t, k - 1);
+                w.head = __ldg(p.R.level_head + g); w.tail = __ldg(p.R.level_tail + g);
                 w.info = __ldg(p.R.level_info + g);
             }
             return w;
@@ -200,36 +231,50 @@ jaccard_allpairs_kernel(const JaccardParams p) {
         const uint32_t lt_begin = lgroup * J_GROUP;
         const uint32_t lt_end = min(lt_begin + (uint32_t)J_GROUP, p.n_ltiles);
         for (uint32_t lt = lt_begin; lt < lt_end; ++lt) {
-            const uint32_t l0 = p.job.l_row_begin + lt * p.tile_left;
-            const uint32_t nl = min(p.tile_left, p.job.l_row_end - l0);
-            const uint32_t G0 = __ldg(p.L.item_level_off + l0);
-            const uint32_t nlev = __ldg(p.L.item_level_off + l0 + nl) - G0;
+            const uint32_t l0 = p.job.l_row_begin + lt * JT_LEFT;
+            const uint32_t nl = min((uint32_t)JT_LEFT, p.job.l_row_end - l0);
 
             __syncthreads();  // previous tile consumed (and the right block staged)
-            for (uint32_t g = tid; g < nlev; g += JT_THREADS) {
-                s.l_head[g] = __ldg(p.L.level_head + G0 + g);
-                s.l_tail[g] = __ldg(p.L.level_tail + G0 + g);
-                s.l_info[g] = __ldg(p.L.level_info + G0 + g);
-                s.l_tok_off[g] = __ldg(p.L.level_tok_off + G0 + g);
+            for (uint32_t e = tid; e < SL * JT_LEFT; e += JT_THREADS) {
+                const uint32_t sl = e / JT_LEFT, li = e % JT_LEFT;
+                uint64_t h = 0, t = 0;
+                uint32_t inf = 0;
+                if (li < nl) {
+                    const size_t at = (size_t)sl * p.L.n_items + l0 + li;
+                    h = __ldg(p.L.slot_head + at);
+                    t = __ldg(p.L.slot_tail + at);
+                    inf = __ldg(p.L.slot_info + at);
+                }
+                s.l_head[sl][li] = h; s.l_tail[sl][li] = t; s.l_info[sl][li] = inf;
             }
-            if (tid == 0) s.l_tok_off[nlev] = __ldg(p.L.level_tok_off + G0 + nlev);
-            if (tid <= nl) s.l_g0[tid] = __ldg(p.L.item_level_off + l0 + tid) - G0;
             if (tid < nl) {
-                s.l_any[tid] = __ldg(reinterpret_cast<const ulonglong2 *>(p.L.item_any) + l0 + tid);
+                s.l_k[tid] = __ldg(p.L.item_k + l0 + tid);
                 s.l_cat[tid] = p.job.cat_mode ? __ldg(p.job.l_cat + l0 + tid) : 0;
+                if (p.any_depth == 0)
+                    s.l_any[tid] = __ldg(reinterpret_cast<const ulonglong2 *>(p.L.item_any) + l0 + tid);
             }
             __syncthreads();
+            if (p.any_depth != 0) {
+                if (tid < nl) {
+                    ulonglong2 any = make_ulonglong2(0, 0);
+                    for (uint32_t sl = 0; sl < min(p.any_depth, SL); ++sl) {
+                        any.x |= s.l_head[sl][tid]; any.y |= s.l_tail[sl][tid];
+                    }
+                    s.l_any[tid] = any;
+                }
+                __syncthreads();
+            }
 
             uint32_t qa_n = 0, qb_n = 0;  // warp-uniform queue fills
 
             // ---- stage C: exact score of one candidate per lane ---------------------------
             auto stage_exact = [&](bool active, uint32_t entry) {
                 const uint32_t li = entry >> 5, rc = (warp << 5) | (entry & 31u);
+                const uint32_t c_l = l0 + li, c_r = r0 + rc;
                 double score = 0.0;
                 bool ok = active;
                 if (active) {
-                    const uint32_t lg0 = s.l_g0[li], kl = s.l_g0[li + 1] - lg0;
-                    const uint32_t c_rg0 = s.r_g0[rc], c_kr = s.r_k[rc];
+                    const uint32_t kl = s.l_k[li], c_kr = s.r_k[rc];
                     ++st_cand;
                     if (kl == 0 || c_kr == 0) {
                         // both empty: compare_terms returns 0; one empty: IndexError in the reference
@@ -237,27 +282,33 @@ jaccard_allpairs_kernel(const JaccardParams p) {
                     } else {
                         const uint32_t kmax = flat ? 1u : max(kl, c_kr);
                         double w = flat ? 2.0 : 1.0;
-                        uint32_t pgl = 0xffffffffu, pgr = 0xffffffffu, inter = 0, uni = 1;
+                        uint32_t pjl = 0xffffffffu, pjr = 0xffffffffu, inter = 0, uni = 1;
                         for (uint32_t t = 1; t <= kmax; ++t) {
-                            const uint32_t gl = lg0 + (flat ? 0u : min(t, kl - 1));
-                            const uint32_t gr = c_rg0 + (flat ? 0u : min(t, c_kr - 1));
+                            const uint32_t jl = flat ? 0u : min(t, kl - 1);
+                            const uint32_t jr = flat ? 0u : min(t, c_kr - 1);
                             ++st_evals;
-                            if (gl != pgl || gr != pgr) {
-                                pgl = gl; pgr = gr;
-                                const LevelWords R = right_level(rc, t, c_rg0, c_kr);
-                                const uint32_t il = s.l_info[gl];
-                                const uint32_t a = il & 0xffffu, b = R.info & 0xffffu;
-                                inter = __popcll(s.l_head[gl] & R.head);
-                                const uint64_t tb = s.l_tail[gl] & R.tail;
+                            if (jl != pjl || jr != pjr) {
+                                pjl = jl; pjr = jr;
+                                const LevelWords A = left_level(li, c_l, t, kl);
+                                const LevelWords B = right_level(rc, c_r, t, c_kr);
+                                const uint32_t a = A.info & 0xffffu, b = B.info & 0xffffu;
+                                inter = __popcll(A.head & B.head);
+                                const uint64_t tb = A.tail & B.tail;
                                 if (tb) {
                                     if (exact_bits) {
                                         inter += __popcll(tb);
-                                    } else {  // ids are sorted: the tail ids follow the n_head head ids
-                                        const uint32_t hl = il >> 24, hr = R.info >> 24;
-                                        inter += merge_count(p.L.tok + s.l_tok_off[gl] + hl, a - hl,
-                                                             p.R.tok + __ldg(p.R.level_tok_off + gr) + hr,
-                                                             b - hr);
-                                        ++st_merges;
+                                    } else {
+                                        const uint32_t gl = __ldg(p.L.item_level_off + c_l) + jl;
+                                        const uint32_t gr = __ldg(p.R.item_level_off + c_r) + jr;
+                                        // a second, independent signature rules most collisions out
+                                        if (__ldg(p.L.level_tail2 + gl) & __ldg(p.R.level_tail2 + gr)) {
+                                            // ids are sorted: the tail ids follow the n_head head ids
+                                            const uint32_t hl = A.info >> 24, hr = B.info >> 24;
+                                            inter += merge_count(
+                                                p.L.tok + __ldg(p.L.level_tok_off + gl) + hl, a - hl,
+                                                p.R.tok + __ldg(p.R.level_tok_off + gr) + hr, b - hr);
+                                            ++st_merges;
+                                        }
                                     }
                                 }
                                 uni = a + b - inter;
@@ -270,7 +321,7 @@ jaccard_allpairs_kernel(const JaccardParams p) {
                         }
                     }
                 }
-                emit(ok && score >= thr, l0 + (entry >> 5), rb * JT_THREADS + rc, score);
+                emit(ok && score >= thr, c_l, c_r, score);
             };
 
             // ---- stage B: fp32 upper bound of one surviving pair per lane -----------------
@@ -278,37 +329,31 @@ jaccard_allpairs_kernel(const JaccardParams p) {
                 const uint32_t li = entry >> 5, rc = (warp << 5) | (entry & 31u);
                 bool pass = active;
                 if (active && !pass_all) {
-                    const uint32_t lg0 = s.l_g0[li], kl = s.l_g0[li + 1] - lg0;
-                    const uint32_t c_rg0 = s.r_g0[rc], c_kr = s.r_k[rc];
+                    const uint32_t kl = s.l_k[li], c_kr = s.r_k[rc];
                     ++st_bound;
                     if (kl != 0 && c_kr != 0) {
                         const uint32_t kmax = flat ? 1u : max(kl, c_kr);
                         const float w_last = flat ? 1.0f : pow2_neg(kmax);
                         float w = flat ? 2.0f : 1.0f, ub = 0.0f;
-                        for (uint32_t t = 1; t <= kmax; ++t) {
-                            const uint32_t gl = lg0 + (flat ? 0u : min(t, kl - 1));
-                            const LevelWords R = right_level(rc, t, c_rg0, c_kr);
-                            const uint32_t il = s.l_info[gl];
-                            const uint32_t a = il & 0xffffu, b = R.info & 0xffffu;
-                            uint32_t ih = __popcll(s.l_head[gl] & R.head);
-                            const uint64_t tb = s.l_tail[gl] & R.tail;
-                            if (tb) {
-                                // shared tail bits + the ids either side folded onto an occupied bit
-                                // bound the shared tail ids (255 = saturated fold count)
-                                const uint32_t ex = min((il >> 16) & 0xffu, (R.info >> 16) & 0xffu);
-                                uint32_t it = exact_bits ? __popcll(tb)
-                                                         : (ex == 255u ? 0xffffu : __popcll(tb) + ex);
-                                it = min(it, min(a - (il >> 24), b - (R.info >> 24)));
-                                ih += it;
-                            }
-                            const uint32_t uh = a + b - ih;
+                        auto step = [&](uint32_t t) {
+                            const LevelWords A = left_level(li, l0 + li, t, kl);
+                            const LevelWords B = right_level(rc, r0 + rc, t, c_kr);
+                            const uint32_t ih = bound_intersection(A, B, exact_bits);
+                            const uint32_t uh = (A.info & 0xffffu) + (B.info & 0xffffu) - ih;
                             w = fmaxf(w * 0.5f, 1.17549435e-38f);
                             if (ih) {
                                 const float rc_up = uh < J_RCP ? s.rcp_up[uh] : __frcp_ru((float)uh);
                                 ub = __fmaf_ru(__fmul_ru((float)ih, rc_up), w, ub);
                             }
-                            // weights still to come: 2^-t - 2^-kmax
-                            if (__fadd_ru(ub, __fsub_ru(w, w_last)) < p.thr_lo) { pass = false; break; }
+                        };
+#pragma unroll
+                        for (uint32_t t = 1; t <= (uint32_t)J_UNROLL; ++t)
+                            if (t <= kmax) step(t);
+                        // weights still to come after step t: 2^-t - 2^-kmax
+                        pass = !(__fadd_ru(ub, __fsub_ru(w, w_last)) < p.thr_lo);
+                        for (uint32_t t = J_UNROLL + 1; pass && t <= kmax; ++t) {
+                            step(t);
+                            pass = !(__fadd_ru(ub, __fsub_ru(w, w_last)) < p.thr_lo);
                         }
                         if (pass) pass = ub >= p.thr_lo;
                     }
@@ -333,8 +378,7 @@ jaccard_allpairs_kernel(const JaccardParams p) {
                 bool pass = r_valid && keep_categories(p.job.cat_mode, s.l_cat[li], rcat);
                 if (pass && !pass_all) {
                     const bool shared = ((lany.x & rany_h) | (lany.y & rany_t)) != 0;
-                    const bool l_empty = s.l_g0[li + 1] == s.l_g0[li];
-                    pass = shared || (l_empty != (kr == 0));  // the latter: IndexError upstream
+                    pass = shared || ((s.l_k[li] == 0) != (kr == 0));  // the latter: IndexError upstream
                 }
                 const unsigned m = __ballot_sync(FULL_MASK, pass);
                 if (m) {
@@ -392,20 +436,27 @@ extern "C" int nsm_jaccard_allpairs(const nsm_sets_t *left, const nsm_sets_t *ri
         set_error("flat scoring needs items with exactly one level");
         return NSM_ERR_BAD_ARG;
     }
-    if (left->max_levels > (uint32_t)J_LCAP) {
-        set_error("left items have up to %u levels; the kernel stages at most %d", left->max_levels,
-                  J_LCAP);
-        return NSM_ERR_UNSUPPORTED;
+    if (left->n_slots < 1 || left->n_slots > (uint32_t)J_SLOTS || right->n_slots < 1 ||
+        right->n_slots > (uint32_t)J_SLOTS) {
+        set_error("n_slots must be in 1..%d", J_SLOTS);
+        return NSM_ERR_BAD_ARG;
     }
 
     JaccardParams p;
     p.L = *left; p.R = *right; p.job = *job;
     p.thr_lo = filter_threshold(job->threshold);
-    const uint32_t kl = left->max_levels ? left->max_levels : 1u;
-    uint32_t tl = (uint32_t)J_LCAP / kl;
-    p.tile_left = tl < 1 ? 1u : (tl > (uint32_t)JT_LEFT ? (uint32_t)JT_LEFT : tl);
+    // stage A depth: the smallest D with 2^-D < threshold, if both sides hold D steps in their
+    // slots (or all their levels); otherwise the packed all-level union is used
+    p.any_depth = 0;
+    if (p.thr_lo > 0.0f && !job->flat) {
+        uint32_t d = 1;
+        while (d < 64 && ldexpf(1.0f, -(int)d) >= p.thr_lo) ++d;
+        const bool l_ok = d <= left->n_slots || left->max_levels <= left->n_slots + 1;
+        const bool r_ok = d <= right->n_slots || right->max_levels <= right->n_slots + 1;
+        if (l_ok && r_ok) p.any_depth = d < (uint32_t)J_SLOTS ? d : (uint32_t)J_SLOTS;
+    }
     const uint32_t n_rows = job->l_row_end - job->l_row_begin;
-    p.n_ltiles = (n_rows + p.tile_left - 1) / p.tile_left;
+    p.n_ltiles = (n_rows + JT_LEFT - 1) / JT_LEFT;
     p.n_lgroups = (p.n_ltiles + J_GROUP - 1) / J_GROUP;
     p.n_rblocks = (right->n_items + JT_THREADS - 1) / JT_THREADS;
     const uint64_t n_units64 = (uint64_t)p.n_lgroups * p.n_rblocks;

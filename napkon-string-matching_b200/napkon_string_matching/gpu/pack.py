@@ -10,9 +10,15 @@ Jaccard operands (``PackedSets``) — one cohort side, CSR over items -> levels 
     level_head      uint64[n_levels]    exact bitset of the level's ids 0..63
     level_tail      uint64[n_levels]    signature of the ids >= 64 (bit = id - 64 if the whole
                                         vocabulary has <= 128 ids, else a multiplicative hash)
+    level_tail2     uint64[n_levels]    a second, independent signature of the ids >= 64
     level_info      uint32[n_levels]    size | min(n_tail - popcount(tail), 255) << 16 | n_head << 24
     item_any        uint64[n_items, 2]  OR of (head, tail) over the levels compare_terms can use
                                         (levels 1..K-1, or level 0 when K == 1)
+    item_k          uint32[n_items]     number of levels K of the item
+    slot_head/tail  uint64[n_slots, n_items]   the summary words again, laid out by compare_terms
+    slot_info       uint32[n_slots, n_items]   step: slot t-1 holds level min(t, K-1) of each item
+                                        (n_slots = clamp(max K - 1, 1, 10); slot-major, so a block of
+                                        consecutive items is contiguous per step)
 
 Token ids are assigned in order of falling frequency over all packed sides, so ids 0..63 (the
 "head") are the 64 most frequent tokens: under the Zipf-like token statistics of questionnaire
@@ -56,8 +62,13 @@ class PackedSets:
     tok: np.ndarray
     level_head: np.ndarray
     level_tail: np.ndarray
+    level_tail2: np.ndarray
     level_info: np.ndarray
     item_any: np.ndarray
+    item_k: np.ndarray
+    slot_head: np.ndarray
+    slot_tail: np.ndarray
+    slot_info: np.ndarray
     n_vocab: int
     exact_bits: bool
     max_levels: int = 0
@@ -72,7 +83,12 @@ class PackedSets:
 
     def arrays(self):
         return [self.item_level_off, self.level_tok_off, self.tok, self.level_head,
-                self.level_tail, self.level_info, self.item_any]
+                self.level_tail, self.level_tail2, self.level_info, self.item_any, self.item_k,
+                self.slot_head, self.slot_tail, self.slot_info]
+
+    @property
+    def n_slots(self) -> int:
+        return self.slot_head.shape[0]
 
     def level_sizes(self) -> np.ndarray:
         return np.diff(self.level_tok_off.astype(np.int64))
@@ -91,7 +107,11 @@ class PackedSets:
             (self.item_level_off[begin : end + 1] - np.uint32(g0)).astype(np.uint32),
             (self.level_tok_off[g0 : g1 + 1] - np.uint32(t0)).astype(np.uint32),
             self.tok[t0:t1].copy(), self.level_head[g0:g1].copy(), self.level_tail[g0:g1].copy(),
-            self.level_info[g0:g1].copy(), self.item_any[begin:end].copy(), self.n_vocab,
+            self.level_tail2[g0:g1].copy(), self.level_info[g0:g1].copy(),
+            self.item_any[begin:end].copy(), self.item_k[begin:end].copy(),
+            np.ascontiguousarray(self.slot_head[:, begin:end]),
+            np.ascontiguousarray(self.slot_tail[:, begin:end]),
+            np.ascontiguousarray(self.slot_info[:, begin:end]), self.n_vocab,
             self.exact_bits, self.max_levels)
 
 
@@ -134,15 +154,17 @@ class PackedStrings:
 # signatures
 # ------------------------------------------------------------------------------------------
 HEAD_IDS = 64
+SLOT_CAP = 10
+SIG2_HASH_MULT = np.uint32(0x85EBCA77)
 
 
-def tail_bits(ids: np.ndarray, exact_bits: bool) -> np.ndarray:
+def tail_bits(ids: np.ndarray, exact_bits: bool, mult=SIG_HASH_MULT) -> np.ndarray:
     """Bit position (0..63) in the tail signature of every token id >= 64."""
     ids = ids.astype(np.uint32, copy=False)
     if exact_bits:
         return (ids - np.uint32(HEAD_IDS)).astype(np.uint64)
     with np.errstate(over="ignore"):
-        return ((ids * SIG_HASH_MULT) >> np.uint32(26)).astype(np.uint64)
+        return ((ids * mult) >> np.uint32(26)).astype(np.uint64)
 
 
 def _segment_or(values: np.ndarray, offsets: np.ndarray) -> np.ndarray:
@@ -170,17 +192,20 @@ def finish_sets(item_level_off, level_tok_off, tok, n_vocab: int) -> PackedSets:
     one = np.uint64(1)
     head_bit = np.where(is_head, np.left_shift(one, np.where(is_head, tok, 0).astype(np.uint64)),
                         np.uint64(0))
-    tail_bit = np.where(is_head, np.uint64(0),
-                        np.left_shift(one, tail_bits(np.where(is_head, HEAD_IDS, tok), exact_bits)))
+    tail_ids = np.where(is_head, HEAD_IDS, tok)
+    tail_bit = np.where(is_head, np.uint64(0), np.left_shift(one, tail_bits(tail_ids, exact_bits)))
+    tail2_bit = np.where(is_head, np.uint64(0),
+                         np.left_shift(one, tail_bits(tail_ids, exact_bits, SIG2_HASH_MULT)))
     head = _segment_or(head_bit, level_tok_off)
     tail = _segment_or(tail_bit, level_tok_off)
+    tail2 = _segment_or(tail2_bit, level_tok_off)
     n_head = np.bitwise_count(head).astype(np.int64)
     extra = np.minimum(sizes - n_head - np.bitwise_count(tail).astype(np.int64), 255)
-    info = sizes.astype(np.uint32) | (extra.astype(np.uint32) << np.uint32(16)) \
-        | (n_head.astype(np.uint32) << np.uint32(24))
+    info = (sizes.astype(np.uint32) | (extra.astype(np.uint32) << np.uint32(16))
+            | (n_head.astype(np.uint32) << np.uint32(24))).astype(np.uint32)
     k = np.diff(item_level_off.astype(np.int64))
-    # union over the levels compare_terms can touch: 1..K-1, or 0 when K == 1
     n_items, n_levels = len(k), len(sizes)
+    # union over the levels compare_terms can touch: 1..K-1, or 0 when K == 1
     item_any = np.zeros((n_items, 2), dtype=np.uint64)
     if n_levels:
         level_item = np.repeat(np.arange(n_items, dtype=np.int64), k)
@@ -188,8 +213,23 @@ def finish_sets(item_level_off, level_tok_off, tok, n_vocab: int) -> PackedSets:
         used = (level_j >= 1) | (k[level_item] == 1)
         np.bitwise_or.at(item_any[:, 0], level_item[used], head[used])
         np.bitwise_or.at(item_any[:, 1], level_item[used], tail[used])
-    return PackedSets(item_level_off, level_tok_off, tok, head, tail, info.astype(np.uint32),
-                      item_any, int(n_vocab), bool(exact_bits), int(k.max()) if len(k) else 0)
+    # compare_terms' schedule, materialised: slot t-1 = level min(t, K-1)
+    max_k = int(k.max()) if n_items else 0
+    n_slots = min(max(max_k - 1, 1), SLOT_CAP)
+    slot_head = np.zeros((n_slots, n_items), dtype=np.uint64)
+    slot_tail = np.zeros((n_slots, n_items), dtype=np.uint64)
+    slot_info = np.zeros((n_slots, n_items), dtype=np.uint32)
+    has = k > 0
+    if n_levels and has.any():
+        base = item_level_off[:-1].astype(np.int64)
+        for t in range(1, n_slots + 1):
+            g = (base + np.minimum(t, np.maximum(k - 1, 0)))[has]
+            slot_head[t - 1, has] = head[g]
+            slot_tail[t - 1, has] = tail[g]
+            slot_info[t - 1, has] = info[g]
+    return PackedSets(item_level_off, level_tok_off, tok, head, tail, tail2, info, item_any,
+                      np.minimum(k, 0xFFFFFFFF).astype(np.uint32), slot_head, slot_tail, slot_info,
+                      int(n_vocab), bool(exact_bits), max_k)
 
 
 def rank_by_frequency(codes_per_side: List[np.ndarray], n_vocab: int) -> List[np.ndarray]:
