@@ -65,12 +65,11 @@ typedef struct nsm_sets {
     const uint64_t *level_head;     /* [n_levels] exact bitset of the level's ids 0..63 */
     const uint64_t *level_tail;     /* [n_levels] signature of its ids >= 64 (exact iff exact_bits) */
     const uint64_t *level_tail2;    /* [n_levels] second, independent signature of the ids >= 64 */
-    const uint32_t *level_info;     /* [n_levels] size | min(n_tail - popc(tail), 255) << 16 | n_head << 24 */
+    const uint32_t *level_info;     /* [n_levels] size | min(n_tail - popc(tail), 255) << 16 */
     const uint64_t *item_any;       /* [n_items][2] OR of (head, tail) over the levels compare_terms uses */
     const uint32_t *item_k;         /* [n_items] number of levels */
-    const uint64_t *slot_head;      /* [n_slots][n_items] level_head of level min(t, K-1), slot t-1 */
-    const uint64_t *slot_tail;      /* [n_slots][n_items] */
-    const uint32_t *slot_info;      /* [n_slots][n_items] */
+    const uint64_t *slot_ht;        /* [n_slots][n_items][2] (head, tail) of level min(t, K-1), slot t-1 */
+    const uint32_t *slot_info;      /* [n_slots][n_items] level_info of the same level */
     uint32_t n_items;
     uint32_t n_levels;
     uint32_t max_levels; /* max levels of any item on this side */

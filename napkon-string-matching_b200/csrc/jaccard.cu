@@ -18,27 +18,28 @@
 //   A  ANY     (per item pair, ~8 integer ops) the OR of the summaries over the first D steps
 //              (2^-D < threshold: later steps cannot lift a zero score over the threshold) shares
 //              no bit => no level pair that matters shares a token => pair proven < threshold.
-//   B  BOUND   (per step, integer + fp32 round-up) exact head intersection by popcount plus an
-//              upper bound of the tail intersection from the signatures bounds every level score;
-//              compare_terms' weights are accumulated with directed rounding.  The first four
-//              steps run as straight-line code, the rest in a loop that stops as soon as
-//              bound + remaining weight cannot reach the threshold.
+//   B  BOUND   (per step, integer + fp32 round-up, branch-free) exact head intersection by
+//              popcount plus an upper bound of the tail intersection from the signatures bounds
+//              every level score; compare_terms' weights are accumulated with directed rounding.
+//              The first four steps run as straight-line code, the rest in a loop that stops as
+//              soon as bound + remaining weight cannot reach the threshold.
 //   C  EXACT   per used level the exact |A & B| (popcount; only if both tail signatures collide,
 //              a merge over the tail ids), the reference's int/int float64 division and its
 //              accumulation order; score >= threshold in float64.
-// Kept pairs go to a per-warp staging buffer and are flushed with one global atomic per ~100
+// Kept pairs go to a per-warp staging buffer and are flushed with one global atomic per ~60
 // records as coalesced 16-byte stores.
 #include "nsm_common.cuh"
 
 namespace nsm {
 
-constexpr int JT_THREADS = 256;  // right items per block (= threads per CTA)
+constexpr int JT_THREADS = 128;  // right items per block (= threads per CTA)
+constexpr int JT_CTAS = 4;       // resident CTAs per SM the kernel is sized for
 constexpr int JT_LEFT = 64;      // left items per tile
 constexpr int J_SLOTS = 10;      // steps staged per item (pack.py SLOT_CAP)
-constexpr int J_GROUP = 8;       // left tiles per unit
+constexpr int J_GROUP = 16;      // left tiles per unit
 constexpr int J_RCP = 512;       // reciprocal table size
 constexpr int J_WARPS = JT_THREADS / 32;
-constexpr int J_OUT = 128;       // staged output records per warp
+constexpr int J_OUT = 96;        // staged output records per warp
 constexpr int J_UNROLL = 4;      // steps of stage B that run as straight-line code
 
 struct JaccardParams {
@@ -50,20 +51,18 @@ struct JaccardParams {
 };
 
 struct __align__(16) JaccardSmem {
-    uint64_t l_head[J_SLOTS][JT_LEFT];
-    uint64_t l_tail[J_SLOTS][JT_LEFT];
-    uint32_t l_info[J_SLOTS][JT_LEFT];
-    uint32_t l_k[JT_LEFT];
+    ulonglong2 l_ht[J_SLOTS][JT_LEFT];  // (head, tail)
+    ulonglong2 r_ht[J_SLOTS][JT_THREADS];
     ulonglong2 l_any[JT_LEFT];
+    nsm_pair_t out[J_WARPS][J_OUT];
     uint64_t l_cat[JT_LEFT];
-    uint64_t r_head[J_SLOTS][JT_THREADS];
-    uint64_t r_tail[J_SLOTS][JT_THREADS];
+    uint32_t l_info[J_SLOTS][JT_LEFT];  // size | fold count << 16
     uint32_t r_info[J_SLOTS][JT_THREADS];
+    uint32_t l_k[JT_LEFT];
     uint32_t r_k[JT_THREADS];
     float rcp_up[J_RCP];
     uint32_t qa[J_WARPS][64];
     uint32_t qb[J_WARPS][64];
-    nsm_pair_t out[J_WARPS][J_OUT];
     unsigned long long stats[NSM_N_STATS];
 };
 
@@ -92,28 +91,21 @@ __device__ __forceinline__ uint32_t merge_count(const uint32_t *__restrict__ a, 
     return c;
 }
 
-struct LevelWords {
-    uint64_t head, tail;
-    uint32_t info;
-};
-
-// upper bound of |A & B| of one level pair from the summaries (exact when the tails share no bit)
-__device__ __forceinline__ uint32_t bound_intersection(const LevelWords &A, const LevelWords &B,
+// Upper bound of |A & B| of one level pair from the summaries; exact when the tails share no
+// bit.  Shared tail bits + the ids either side folded onto an occupied bit bound the shared tail
+// ids (a fold count of 255 is saturated: fall back to min(|A|, |B|)).  Branch-free.
+__device__ __forceinline__ uint32_t bound_intersection(const ulonglong2 &A, uint32_t ia,
+                                                       const ulonglong2 &B, uint32_t ib,
                                                        bool exact_bits) {
-    uint32_t ih = __popcll(A.head & B.head);
-    const uint64_t tb = A.tail & B.tail;
-    if (tb) {
-        // shared tail bits + the ids either side folded onto an occupied bit bound the shared
-        // tail ids (255 = saturated fold count)
-        const uint32_t ex = min((A.info >> 16) & 0xffu, (B.info >> 16) & 0xffu);
-        uint32_t it = exact_bits ? __popcll(tb) : (ex == 255u ? 0xffffu : __popcll(tb) + ex);
-        it = min(it, min((A.info & 0xffffu) - (A.info >> 24), (B.info & 0xffffu) - (B.info >> 24)));
-        ih += it;
-    }
-    return ih;
+    const uint64_t tb = A.y & B.y;
+    const uint32_t ex = min(ia >> 16, ib >> 16);
+    uint32_t it = __popcll(tb) + (exact_bits ? 0u : ex + (ex == 255u ? 0x10000u : 0u));
+    it = tb ? it : 0u;
+    return min(__popcll(A.x & B.x) + it, min(ia & 0xffffu, ib & 0xffffu));
 }
 
-__global__ void __launch_bounds__(JT_THREADS, 2)
+template <bool DEEP>
+__global__ void __launch_bounds__(JT_THREADS, JT_CTAS)
 jaccard_allpairs_kernel(const JaccardParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     JaccardSmem &s = *reinterpret_cast<JaccardSmem *>(smem_raw);
@@ -125,14 +117,12 @@ jaccard_allpairs_kernel(const JaccardParams p) {
     const double thr = p.job.threshold;
     const bool pass_all = !(p.thr_lo > -INFINITY) && !(p.thr_lo != p.thr_lo);  // thr <= 0
     const uint32_t SL = p.L.n_slots, SR = p.R.n_slots;
-    // an item whose levels do not all fit its side's slots needs the CSR arrays for deep steps
-    const bool l_deep = p.L.max_levels > SL + 1, r_deep = p.R.max_levels > SR + 1;
 
     for (unsigned u = tid; u < J_RCP; u += JT_THREADS) s.rcp_up[u] = u ? __frcp_ru((float)u) : 0.0f;
     if (tid < NSM_N_STATS) s.stats[tid] = 0;
     unsigned long long st_cand = 0, st_evals = 0, st_merges = 0, st_bound = 0;
-
     uint32_t out_n = 0;  // warp-uniform fill of s.out[warp]
+
     auto flush_out = [&]() {
         if (out_n == 0) return;
         unsigned long long base = 0;
@@ -149,19 +139,28 @@ jaccard_allpairs_kernel(const JaccardParams p) {
         __syncwarp();
         out_n = 0;
     };
-    auto emit = [&](bool keep, uint32_t left, uint32_t right, double score) {  // all 32 lanes
-        const unsigned m = __ballot_sync(FULL_MASK, keep);
-        if (m == 0) return;
-        const uint32_t n = __popc(m);
-        if (out_n + n > J_OUT) flush_out();
-        if (keep) {
-            double2 rec;
-            rec.x = __longlong_as_double((long long)(((unsigned long long)right << 32) | left));
-            rec.y = score;
-            reinterpret_cast<double2 *>(&s.out[warp][0])[out_n + __popc(m & lanemask_lt())] = rec;
+
+    // summary of item `col` of the staged tile/block at step t >= 1 (CSR arrays when the item
+    // has more levels than slots and t lies beyond them)
+    auto left_level = [&](uint32_t li, uint32_t item, uint32_t t, uint32_t k, uint32_t &info) {
+        if (DEEP && t > SL && k > SL + 1) {
+            const uint32_t g = __ldg(p.L.item_level_off + item) + min(t, k - 1);
+            info = __ldg(p.L.level_info + g);
+            return make_ulonglong2(__ldg(p.L.level_head + g), __ldg(p.L.level_tail + g));
         }
-        out_n += n;
-        __syncwarp();
+        const uint32_t sl = min(t, SL) - 1;
+        info = s.l_info[sl][li];
+        return s.l_ht[sl][li];
+    };
+    auto right_level = [&](uint32_t rc, uint32_t item, uint32_t t, uint32_t k, uint32_t &info) {
+        if (DEEP && t > SR && k > SR + 1) {
+            const uint32_t g = __ldg(p.R.item_level_off + item) + min(t, k - 1);
+            info = __ldg(p.R.level_info + g);
+            return make_ulonglong2(__ldg(p.R.level_head + g), __ldg(p.R.level_tail + g));
+        }
+        const uint32_t sr = min(t, SR) - 1;
+        info = s.r_info[sr][rc];
+        return s.r_ht[sr][rc];
     };
 
     const uint32_t n_units = p.n_lgroups * p.n_rblocks;
@@ -183,50 +182,22 @@ jaccard_allpairs_kernel(const JaccardParams p) {
 #pragma unroll
         for (int sl = 0; sl < J_SLOTS; ++sl) {
             if ((uint32_t)sl < SR) {
-                uint64_t h = 0, t = 0;
+                ulonglong2 ht = make_ulonglong2(0, 0);
                 uint32_t inf = 0;
                 if (r_valid) {
                     const size_t at = (size_t)sl * p.R.n_items + r;
-                    h = __ldg(p.R.slot_head + at);
-                    t = __ldg(p.R.slot_tail + at);
+                    ht = __ldg(reinterpret_cast<const ulonglong2 *>(p.R.slot_ht) + at);
                     inf = __ldg(p.R.slot_info + at);
                 }
-                s.r_head[sl][tid] = h;
-                s.r_tail[sl][tid] = t;
+                s.r_ht[sl][tid] = ht;
                 s.r_info[sl][tid] = inf;
-                if ((uint32_t)sl < p.any_depth) { rany_h |= h; rany_t |= t; }
+                if ((uint32_t)sl < p.any_depth) { rany_h |= ht.x; rany_t |= ht.y; }
             }
         }
         if (p.any_depth == 0 && r_valid) {
             const ulonglong2 any = __ldg(reinterpret_cast<const ulonglong2 *>(p.R.item_any) + r);
             rany_h = any.x; rany_t = any.y;
         }
-
-        // summary words of one item at step t (t >= 1); col = column in the staged block
-        auto left_level = [&](uint32_t li, uint32_t item, uint32_t t, uint32_t k) {
-            LevelWords w;
-            if (!l_deep || t <= SL || k <= SL + 1) {
-                const uint32_t sl = min(t, SL) - 1;
-                w.head = s.l_head[sl][li]; w.tail = s.l_tail[sl][li]; w.info = s.l_info[sl][li];
-            } else {
-                const uint32_t g = __ldg(p.L.item_level_off + item) + min(t, k - 1);
-                w.head = __ldg(p.L.level_head + g); w.tail = __ldg(p.L.level_tail + g);
-                w.info = __ldg(p.L.level_info + g);
-            }
-            return w;
-        };
-        auto right_level = [&](uint32_t rc, uint32_t item, uint32_t t, uint32_t k) {
-            LevelWords w;
-            if (!r_deep || t <= SR || k <= SR + 1) {
-                const uint32_t sl = min(t, SR) - 1;
-                w.head = s.r_head[sl][rc]; w.tail = s.r_tail[sl][rc]; w.info = s.r_info[sl][rc];
-            } else {
-                const uint32_t g = __ldg(p.R.item_level_off + item) + min(t, k - 1);
-                w.head = __ldg(p.R.level_head + g); w.tail = __ldg(p.R.level_tail + g);
-                w.info = __ldg(p.R.level_info + g);
-            }
-            return w;
-        };
 
         const uint32_t lt_begin = lgroup * J_GROUP;
         const uint32_t lt_end = min(lt_begin + (uint32_t)J_GROUP, p.n_ltiles);
@@ -237,15 +208,15 @@ jaccard_allpairs_kernel(const JaccardParams p) {
             __syncthreads();  // previous tile consumed (and the right block staged)
             for (uint32_t e = tid; e < SL * JT_LEFT; e += JT_THREADS) {
                 const uint32_t sl = e / JT_LEFT, li = e % JT_LEFT;
-                uint64_t h = 0, t = 0;
+                ulonglong2 ht = make_ulonglong2(0, 0);
                 uint32_t inf = 0;
                 if (li < nl) {
                     const size_t at = (size_t)sl * p.L.n_items + l0 + li;
-                    h = __ldg(p.L.slot_head + at);
-                    t = __ldg(p.L.slot_tail + at);
+                    ht = __ldg(reinterpret_cast<const ulonglong2 *>(p.L.slot_ht) + at);
                     inf = __ldg(p.L.slot_info + at);
                 }
-                s.l_head[sl][li] = h; s.l_tail[sl][li] = t; s.l_info[sl][li] = inf;
+                s.l_ht[sl][li] = ht;
+                s.l_info[sl][li] = inf;
             }
             if (tid < nl) {
                 s.l_k[tid] = __ldg(p.L.item_k + l0 + tid);
@@ -258,155 +229,161 @@ jaccard_allpairs_kernel(const JaccardParams p) {
                 if (tid < nl) {
                     ulonglong2 any = make_ulonglong2(0, 0);
                     for (uint32_t sl = 0; sl < min(p.any_depth, SL); ++sl) {
-                        any.x |= s.l_head[sl][tid]; any.y |= s.l_tail[sl][tid];
+                        any.x |= s.l_ht[sl][tid].x; any.y |= s.l_ht[sl][tid].y;
                     }
                     s.l_any[tid] = any;
                 }
                 __syncthreads();
             }
 
-            uint32_t qa_n = 0, qb_n = 0;  // warp-uniform queue fills
-
-            // ---- stage C: exact score of one candidate per lane ---------------------------
-            auto stage_exact = [&](bool active, uint32_t entry) {
-                const uint32_t li = entry >> 5, rc = (warp << 5) | (entry & 31u);
-                const uint32_t c_l = l0 + li, c_r = r0 + rc;
-                double score = 0.0;
-                bool ok = active;
-                if (active) {
-                    const uint32_t kl = s.l_k[li], c_kr = s.r_k[rc];
-                    ++st_cand;
-                    if (kl == 0 || c_kr == 0) {
-                        // both empty: compare_terms returns 0; one empty: IndexError in the reference
-                        if (kl != c_kr) { atomicOr(p.job.out_flags, NSM_FLAG_EMPTY_ITEM); ok = false; }
-                    } else {
-                        const uint32_t kmax = flat ? 1u : max(kl, c_kr);
-                        double w = flat ? 2.0 : 1.0;
-                        uint32_t pjl = 0xffffffffu, pjr = 0xffffffffu, inter = 0, uni = 1;
-                        for (uint32_t t = 1; t <= kmax; ++t) {
-                            const uint32_t jl = flat ? 0u : min(t, kl - 1);
-                            const uint32_t jr = flat ? 0u : min(t, c_kr - 1);
-                            ++st_evals;
-                            if (jl != pjl || jr != pjr) {
-                                pjl = jl; pjr = jr;
-                                const LevelWords A = left_level(li, c_l, t, kl);
-                                const LevelWords B = right_level(rc, c_r, t, c_kr);
-                                const uint32_t a = A.info & 0xffffu, b = B.info & 0xffffu;
-                                inter = __popcll(A.head & B.head);
-                                const uint64_t tb = A.tail & B.tail;
-                                if (tb) {
-                                    if (exact_bits) {
-                                        inter += __popcll(tb);
-                                    } else {
-                                        const uint32_t gl = __ldg(p.L.item_level_off + c_l) + jl;
-                                        const uint32_t gr = __ldg(p.R.item_level_off + c_r) + jr;
-                                        // a second, independent signature rules most collisions out
-                                        if (__ldg(p.L.level_tail2 + gl) & __ldg(p.R.level_tail2 + gr)) {
-                                            // ids are sorted: the tail ids follow the n_head head ids
-                                            const uint32_t hl = A.info >> 24, hr = B.info >> 24;
-                                            inter += merge_count(
-                                                p.L.tok + __ldg(p.L.level_tok_off + gl) + hl, a - hl,
-                                                p.R.tok + __ldg(p.R.level_tok_off + gr) + hr, b - hr);
-                                            ++st_merges;
-                                        }
-                                    }
-                                }
-                                uni = a + b - inter;
-                            }
-                            w *= 0.5;
-                            // len(A & B) / len(A | B): int / int true division, then score += s * w
-                            const double sc = __ddiv_rn((double)inter, (double)uni);
-                            if (uni == 0) { atomicOr(p.job.out_flags, NSM_FLAG_ZERO_UNION); ok = false; }
-                            score = __fma_rn(sc, w, score);
-                        }
+            // The funnel as one loop, so that each stage's code exists once: fill queue A from
+            // stage A until it holds a warp's worth (or the tile is exhausted), run stage B on 32
+            // entries, run stage C whenever queue B holds 32 (or everything before it is done).
+            uint32_t qa_n = 0, qb_n = 0, li_next = 0;  // warp-uniform
+            while (true) {
+                // ---- stage A: one left item x my right item -------------------------------
+                while (qa_n < 32 && li_next < nl) {
+                    const uint32_t li = li_next++;
+                    const ulonglong2 lany = s.l_any[li];
+                    bool pass = r_valid && keep_categories(p.job.cat_mode, s.l_cat[li], rcat);
+                    if (!pass_all) {
+                        const bool shared = ((lany.x & rany_h) | (lany.y & rany_t)) != 0;
+                        // an empty item against a non-empty one is an IndexError upstream
+                        pass = pass && (shared || ((s.l_k[li] == 0) != (kr == 0)));
                     }
+                    const unsigned m = __ballot_sync(FULL_MASK, pass);
+                    if (pass) s.qa[warp][qa_n + __popc(m & lanemask_lt())] = (li << 5) | lane;
+                    qa_n += __popc(m);
                 }
-                emit(ok && score >= thr, c_l, c_r, score);
-            };
+                const bool tile_done = li_next >= nl;
+                if (qa_n == 0 && qb_n == 0 && tile_done) break;
+                __syncwarp();
 
-            // ---- stage B: fp32 upper bound of one surviving pair per lane -----------------
-            auto stage_bound = [&](bool active, uint32_t entry) {
-                const uint32_t li = entry >> 5, rc = (warp << 5) | (entry & 31u);
-                bool pass = active;
-                if (active && !pass_all) {
+                // ---- stage B: fp32 upper bound of one surviving pair per lane -------------
+                if (qa_n >= 32 || (tile_done && qa_n)) {
+                    const uint32_t take = min(qa_n, 32u);
+                    qa_n -= take;
+                    const bool active = lane < take;
+                    const uint32_t entry = active ? s.qa[warp][qa_n + lane] : 0u;
+                    const uint32_t li = entry >> 5, rc = (warp << 5) | (entry & 31u);
                     const uint32_t kl = s.l_k[li], c_kr = s.r_k[rc];
-                    ++st_bound;
-                    if (kl != 0 && c_kr != 0) {
+                    bool pass = active;
+                    if (active && !pass_all && kl != 0 && c_kr != 0) {
                         const uint32_t kmax = flat ? 1u : max(kl, c_kr);
-                        const float w_last = flat ? 1.0f : pow2_neg(kmax);
-                        float w = flat ? 2.0f : 1.0f, ub = 0.0f;
-                        auto step = [&](uint32_t t) {
-                            const LevelWords A = left_level(li, l0 + li, t, kl);
-                            const LevelWords B = right_level(rc, r0 + rc, t, c_kr);
-                            const uint32_t ih = bound_intersection(A, B, exact_bits);
-                            const uint32_t uh = (A.info & 0xffffu) + (B.info & 0xffffu) - ih;
-                            w = fmaxf(w * 0.5f, 1.17549435e-38f);
-                            if (ih) {
-                                const float rc_up = uh < J_RCP ? s.rcp_up[uh] : __frcp_ru((float)uh);
-                                ub = __fmaf_ru(__fmul_ru((float)ih, rc_up), w, ub);
-                            }
-                        };
+                        float ub = 0.0f;
+                        ++st_bound;
 #pragma unroll
-                        for (uint32_t t = 1; t <= (uint32_t)J_UNROLL; ++t)
-                            if (t <= kmax) step(t);
-                        // weights still to come after step t: 2^-t - 2^-kmax
-                        pass = !(__fadd_ru(ub, __fsub_ru(w, w_last)) < p.thr_lo);
-                        for (uint32_t t = J_UNROLL + 1; pass && t <= kmax; ++t) {
-                            step(t);
-                            pass = !(__fadd_ru(ub, __fsub_ru(w, w_last)) < p.thr_lo);
+                        for (uint32_t t = 1; t <= (uint32_t)J_UNROLL; ++t) {
+                            // steps beyond kmax read a repeated level and get weight 0
+                            const uint32_t sl = min(t, SL) - 1, sr = min(t, SR) - 1;
+                            const uint32_t ia = s.l_info[sl][li], ib = s.r_info[sr][rc];
+                            const uint32_t ih = bound_intersection(s.l_ht[sl][li], ia, s.r_ht[sr][rc],
+                                                                   ib, exact_bits);
+                            const uint32_t uh = min((ia & 0xffffu) + (ib & 0xffffu) - ih,
+                                                    (uint32_t)J_RCP - 1);  // 1/511 >= 1/u beyond
+                            const float w = t <= kmax ? (flat ? 1.0f : pow2_neg(t)) : 0.0f;
+                            ub = __fmaf_ru(__fmul_ru((float)ih, s.rcp_up[uh]), w, ub);
                         }
-                        if (pass) pass = ub >= p.thr_lo;
+                        if (kmax > (uint32_t)J_UNROLL) {
+                            const float w_last = pow2_neg(kmax);
+                            float w = pow2_neg(J_UNROLL);
+                            // weights still to come after step t: 2^-t - 2^-kmax
+                            pass = !(__fadd_ru(ub, __fsub_ru(w, w_last)) < p.thr_lo);
+                            for (uint32_t t = J_UNROLL + 1; pass && t <= kmax; ++t) {
+                                uint32_t ia, ib;
+                                const ulonglong2 A = left_level(li, l0 + li, t, kl, ia);
+                                const ulonglong2 B = right_level(rc, r0 + rc, t, c_kr, ib);
+                                const uint32_t ih = bound_intersection(A, ia, B, ib, exact_bits);
+                                const uint32_t uh = min((ia & 0xffffu) + (ib & 0xffffu) - ih,
+                                                        (uint32_t)J_RCP - 1);
+                                w = fmaxf(w * 0.5f, 1.17549435e-38f);
+                                ub = __fmaf_ru(__fmul_ru((float)ih, s.rcp_up[uh]), w, ub);
+                                pass = !(__fadd_ru(ub, __fsub_ru(w, w_last)) < p.thr_lo);
+                            }
+                        }
+                        pass = pass && ub >= p.thr_lo;
                     }
-                }
-                const unsigned m = __ballot_sync(FULL_MASK, pass);
-                if (m) {
+                    const unsigned m = __ballot_sync(FULL_MASK, pass);
                     if (pass) s.qb[warp][qb_n + __popc(m & lanemask_lt())] = entry;
                     qb_n += __popc(m);
                     __syncwarp();
-                    if (qb_n >= 32) {
-                        qb_n -= 32;
-                        const uint32_t e = s.qb[warp][qb_n + lane];
-                        __syncwarp();
-                        stage_exact(true, e);
-                    }
                 }
-            };
 
-            // ---- stage A: one left item x my right item ------------------------------------
-            for (uint32_t li = 0; li < nl; ++li) {
-                const ulonglong2 lany = s.l_any[li];
-                bool pass = r_valid && keep_categories(p.job.cat_mode, s.l_cat[li], rcat);
-                if (pass && !pass_all) {
-                    const bool shared = ((lany.x & rany_h) | (lany.y & rany_t)) != 0;
-                    pass = shared || ((s.l_k[li] == 0) != (kr == 0));  // the latter: IndexError upstream
-                }
-                const unsigned m = __ballot_sync(FULL_MASK, pass);
-                if (m) {
-                    if (pass) s.qa[warp][qa_n + __popc(m & lanemask_lt())] = (li << 5) | lane;
-                    qa_n += __popc(m);
-                    __syncwarp();
-                    if (qa_n >= 32) {
-                        qa_n -= 32;
-                        const uint32_t e = s.qa[warp][qa_n + lane];
-                        __syncwarp();
-                        stage_bound(true, e);
+                // ---- stage C: exact score of one candidate per lane -----------------------
+                if (qb_n >= 32 || (tile_done && qa_n == 0 && qb_n)) {
+                    const uint32_t take = min(qb_n, 32u);
+                    qb_n -= take;
+                    const bool active = lane < take;
+                    const uint32_t entry = active ? s.qb[warp][qb_n + lane] : 0u;
+                    const uint32_t li = entry >> 5, rc = (warp << 5) | (entry & 31u);
+                    const uint32_t c_l = l0 + li, c_r = r0 + rc;
+                    double score = 0.0;
+                    bool ok = active;
+                    if (active) {
+                        const uint32_t kl = s.l_k[li], c_kr = s.r_k[rc];
+                        ++st_cand;
+                        if (kl == 0 || c_kr == 0) {
+                            // both empty: compare_terms returns 0; one empty: IndexError upstream
+                            if (kl != c_kr) { atomicOr(p.job.out_flags, NSM_FLAG_EMPTY_ITEM); ok = false; }
+                        } else {
+                            const uint32_t kmax = flat ? 1u : max(kl, c_kr);
+                            double w = flat ? 2.0 : 1.0;
+                            uint32_t pjl = 0xffffffffu, pjr = 0xffffffffu, inter = 0, uni = 1;
+                            for (uint32_t t = 1; t <= kmax; ++t) {
+                                const uint32_t jl = flat ? 0u : min(t, kl - 1);
+                                const uint32_t jr = flat ? 0u : min(t, c_kr - 1);
+                                ++st_evals;
+                                if (jl != pjl || jr != pjr) {
+                                    pjl = jl; pjr = jr;
+                                    uint32_t ia, ib;
+                                    const ulonglong2 A = left_level(li, c_l, t, kl, ia);
+                                    const ulonglong2 B = right_level(rc, c_r, t, c_kr, ib);
+                                    const uint32_t a = ia & 0xffffu, b = ib & 0xffffu;
+                                    inter = __popcll(A.x & B.x);
+                                    const uint64_t tb = A.y & B.y;
+                                    if (tb) {
+                                        if (exact_bits) {
+                                            inter += __popcll(tb);
+                                        } else {
+                                            const uint32_t gl = __ldg(p.L.item_level_off + c_l) + jl;
+                                            const uint32_t gr = __ldg(p.R.item_level_off + c_r) + jr;
+                                            // a second, independent signature rules most collisions out
+                                            if (__ldg(p.L.level_tail2 + gl) & __ldg(p.R.level_tail2 + gr)) {
+                                                // ids are sorted: the tail ids follow the head ids
+                                                const uint32_t hl = __popcll(A.x), hr = __popcll(B.x);
+                                                inter += merge_count(
+                                                    p.L.tok + __ldg(p.L.level_tok_off + gl) + hl, a - hl,
+                                                    p.R.tok + __ldg(p.R.level_tok_off + gr) + hr, b - hr);
+                                                ++st_merges;
+                                            }
+                                        }
+                                    }
+                                    uni = a + b - inter;
+                                }
+                                w *= 0.5;
+                                // len(A & B) / len(A | B): int / int true division; score += s * w
+                                const double sc = __ddiv_rn((double)inter, (double)uni);
+                                if (uni == 0) { atomicOr(p.job.out_flags, NSM_FLAG_ZERO_UNION); ok = false; }
+                                score = __fma_rn(sc, w, score);
+                            }
+                        }
                     }
+                    // ---- threshold compaction into the warp's staging buffer ---------------
+                    const bool keep = ok && score >= thr;
+                    const unsigned m = __ballot_sync(FULL_MASK, keep);
+                    if (m) {
+                        const uint32_t n = __popc(m);
+                        if (out_n + n > J_OUT) flush_out();
+                        if (keep) {
+                            double2 rec;
+                            rec.x = __longlong_as_double((long long)(((unsigned long long)c_r << 32) | c_l));
+                            rec.y = score;
+                            reinterpret_cast<double2 *>(&s.out[warp][0])[out_n + __popc(m & lanemask_lt())] = rec;
+                        }
+                        out_n += n;
+                    }
+                    __syncwarp();
                 }
-            }
-            // drain what is left of both queues before the tile is replaced
-            if (qa_n) {
-                const bool active = lane < qa_n;
-                const uint32_t e = active ? s.qa[warp][lane] : 0u;
-                __syncwarp();
-                qa_n = 0;
-                stage_bound(active, e);
-            }
-            if (qb_n) {
-                const bool active = lane < qb_n;
-                const uint32_t e = active ? s.qb[warp][lane] : 0u;
-                __syncwarp();
-                qb_n = 0;
-                stage_exact(active, e);
             }
         }
     }
@@ -421,6 +398,18 @@ jaccard_allpairs_kernel(const JaccardParams p) {
         if (tid < NSM_N_STATS && s.stats[tid])
             atomicAdd(reinterpret_cast<unsigned long long *>(p.job.out_stats) + tid, s.stats[tid]);
     }
+}
+
+template <bool DEEP>
+static int launch_jaccard(const JaccardParams &p, uint64_t n_units, cudaStream_t stream) {
+    const size_t smem = sizeof(JaccardSmem);
+    NSM_CUDA_CHECK(cudaFuncSetAttribute(jaccard_allpairs_kernel<DEEP>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint64_t resident = (uint64_t)JT_CTAS * (uint64_t)sm_count();
+    const uint32_t grid = (uint32_t)(n_units < resident ? n_units : resident);
+    jaccard_allpairs_kernel<DEEP><<<grid, JT_THREADS, smem, stream>>>(p);
+    NSM_CUDA_CHECK(cudaGetLastError());
+    return NSM_OK;
 }
 
 }  // namespace nsm
@@ -445,37 +434,27 @@ extern "C" int nsm_jaccard_allpairs(const nsm_sets_t *left, const nsm_sets_t *ri
     JaccardParams p;
     p.L = *left; p.R = *right; p.job = *job;
     p.thr_lo = filter_threshold(job->threshold);
+    // an item whose levels do not all fit its side's slots needs the CSR arrays for deep steps
+    const bool l_deep = left->max_levels > left->n_slots + 1;
+    const bool r_deep = right->max_levels > right->n_slots + 1;
     // stage A depth: the smallest D with 2^-D < threshold, if both sides hold D steps in their
     // slots (or all their levels); otherwise the packed all-level union is used
     p.any_depth = 0;
     if (p.thr_lo > 0.0f && !job->flat) {
         uint32_t d = 1;
         while (d < 64 && ldexpf(1.0f, -(int)d) >= p.thr_lo) ++d;
-        const bool l_ok = d <= left->n_slots || left->max_levels <= left->n_slots + 1;
-        const bool r_ok = d <= right->n_slots || right->max_levels <= right->n_slots + 1;
-        if (l_ok && r_ok) p.any_depth = d < (uint32_t)J_SLOTS ? d : (uint32_t)J_SLOTS;
+        if ((d <= left->n_slots || !l_deep) && (d <= right->n_slots || !r_deep))
+            p.any_depth = d < (uint32_t)J_SLOTS ? d : (uint32_t)J_SLOTS;
     }
     const uint32_t n_rows = job->l_row_end - job->l_row_begin;
     p.n_ltiles = (n_rows + JT_LEFT - 1) / JT_LEFT;
     p.n_lgroups = (p.n_ltiles + J_GROUP - 1) / J_GROUP;
     p.n_rblocks = (right->n_items + JT_THREADS - 1) / JT_THREADS;
-    const uint64_t n_units64 = (uint64_t)p.n_lgroups * p.n_rblocks;
-    if (n_units64 > 0xffffffffull) {
-        set_error("too many work units (%llu); split the left row block",
-                  (unsigned long long)n_units64);
+    const uint64_t n_units = (uint64_t)p.n_lgroups * p.n_rblocks;
+    if (n_units > 0xffffffffull) {
+        set_error("too many work units (%llu); split the left row block", (unsigned long long)n_units);
         return NSM_ERR_UNSUPPORTED;
     }
-
-    static bool attr_set = false;
-    const size_t smem = sizeof(JaccardSmem);
-    if (!attr_set) {
-        NSM_CUDA_CHECK(cudaFuncSetAttribute(jaccard_allpairs_kernel,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
-    const uint32_t resident = 2u * (uint32_t)sm_count();  // __launch_bounds__(.., 2)
-    const uint32_t grid = (uint32_t)(n_units64 < resident ? n_units64 : resident);
-    jaccard_allpairs_kernel<<<grid, JT_THREADS, smem, stream>>>(p);
-    NSM_CUDA_CHECK(cudaGetLastError());
-    return NSM_OK;
+    return (l_deep || r_deep) ? launch_jaccard<true>(p, n_units, stream)
+                              : launch_jaccard<false>(p, n_units, stream);
 }

@@ -11,12 +11,12 @@ Jaccard operands (``PackedSets``) — one cohort side, CSR over items -> levels 
     level_tail      uint64[n_levels]    signature of the ids >= 64 (bit = id - 64 if the whole
                                         vocabulary has <= 128 ids, else a multiplicative hash)
     level_tail2     uint64[n_levels]    a second, independent signature of the ids >= 64
-    level_info      uint32[n_levels]    size | min(n_tail - popcount(tail), 255) << 16 | n_head << 24
+    level_info      uint32[n_levels]    size | min(n_tail - popcount(tail), 255) << 16
     item_any        uint64[n_items, 2]  OR of (head, tail) over the levels compare_terms can use
                                         (levels 1..K-1, or level 0 when K == 1)
     item_k          uint32[n_items]     number of levels K of the item
-    slot_head/tail  uint64[n_slots, n_items]   the summary words again, laid out by compare_terms
-    slot_info       uint32[n_slots, n_items]   step: slot t-1 holds level min(t, K-1) of each item
+    slot_ht         uint64[n_slots, n_items, 2]  (head, tail) again, laid out by compare_terms step:
+    slot_info       uint32[n_slots, n_items]     slot t-1 holds level min(t, K-1) of each item
                                         (n_slots = clamp(max K - 1, 1, 10); slot-major, so a block of
                                         consecutive items is contiguous per step)
 
@@ -66,8 +66,7 @@ class PackedSets:
     level_info: np.ndarray
     item_any: np.ndarray
     item_k: np.ndarray
-    slot_head: np.ndarray
-    slot_tail: np.ndarray
+    slot_ht: np.ndarray
     slot_info: np.ndarray
     n_vocab: int
     exact_bits: bool
@@ -84,11 +83,11 @@ class PackedSets:
     def arrays(self):
         return [self.item_level_off, self.level_tok_off, self.tok, self.level_head,
                 self.level_tail, self.level_tail2, self.level_info, self.item_any, self.item_k,
-                self.slot_head, self.slot_tail, self.slot_info]
+                self.slot_ht, self.slot_info]
 
     @property
     def n_slots(self) -> int:
-        return self.slot_head.shape[0]
+        return self.slot_ht.shape[0]
 
     def level_sizes(self) -> np.ndarray:
         return np.diff(self.level_tok_off.astype(np.int64))
@@ -109,8 +108,7 @@ class PackedSets:
             self.tok[t0:t1].copy(), self.level_head[g0:g1].copy(), self.level_tail[g0:g1].copy(),
             self.level_tail2[g0:g1].copy(), self.level_info[g0:g1].copy(),
             self.item_any[begin:end].copy(), self.item_k[begin:end].copy(),
-            np.ascontiguousarray(self.slot_head[:, begin:end]),
-            np.ascontiguousarray(self.slot_tail[:, begin:end]),
+            np.ascontiguousarray(self.slot_ht[:, begin:end]),
             np.ascontiguousarray(self.slot_info[:, begin:end]), self.n_vocab,
             self.exact_bits, self.max_levels)
 
@@ -201,8 +199,7 @@ def finish_sets(item_level_off, level_tok_off, tok, n_vocab: int) -> PackedSets:
     tail2 = _segment_or(tail2_bit, level_tok_off)
     n_head = np.bitwise_count(head).astype(np.int64)
     extra = np.minimum(sizes - n_head - np.bitwise_count(tail).astype(np.int64), 255)
-    info = (sizes.astype(np.uint32) | (extra.astype(np.uint32) << np.uint32(16))
-            | (n_head.astype(np.uint32) << np.uint32(24))).astype(np.uint32)
+    info = (sizes.astype(np.uint32) | (extra.astype(np.uint32) << np.uint32(16))).astype(np.uint32)
     k = np.diff(item_level_off.astype(np.int64))
     n_items, n_levels = len(k), len(sizes)
     # union over the levels compare_terms can touch: 1..K-1, or 0 when K == 1
@@ -216,19 +213,18 @@ def finish_sets(item_level_off, level_tok_off, tok, n_vocab: int) -> PackedSets:
     # compare_terms' schedule, materialised: slot t-1 = level min(t, K-1)
     max_k = int(k.max()) if n_items else 0
     n_slots = min(max(max_k - 1, 1), SLOT_CAP)
-    slot_head = np.zeros((n_slots, n_items), dtype=np.uint64)
-    slot_tail = np.zeros((n_slots, n_items), dtype=np.uint64)
+    slot_ht = np.zeros((n_slots, n_items, 2), dtype=np.uint64)
     slot_info = np.zeros((n_slots, n_items), dtype=np.uint32)
     has = k > 0
     if n_levels and has.any():
         base = item_level_off[:-1].astype(np.int64)
         for t in range(1, n_slots + 1):
             g = (base + np.minimum(t, np.maximum(k - 1, 0)))[has]
-            slot_head[t - 1, has] = head[g]
-            slot_tail[t - 1, has] = tail[g]
+            slot_ht[t - 1, has, 0] = head[g]
+            slot_ht[t - 1, has, 1] = tail[g]
             slot_info[t - 1, has] = info[g]
     return PackedSets(item_level_off, level_tok_off, tok, head, tail, tail2, info, item_any,
-                      np.minimum(k, 0xFFFFFFFF).astype(np.uint32), slot_head, slot_tail, slot_info,
+                      np.minimum(k, 0xFFFFFFFF).astype(np.uint32), slot_ht, slot_info,
                       int(n_vocab), bool(exact_bits), max_k)
 
 

@@ -131,7 +131,7 @@ def test_pack_sets_layout_and_signatures():
             toks = p.tok[p.level_tok_off[g]:p.level_tok_off[g + 1]]
             assert list(toks) == sorted(set(toks))
             assert int(p.level_head[g]) == sum(1 << int(t) for t in toks) and p.level_tail[g] == 0
-            assert p.level_info[g] & 0xFFFF == len(toks) and p.level_info[g] >> 24 == len(toks)
+            assert p.level_info[g] & 0xFFFF == len(toks) and p.level_info[g] >> 16 == 0
     # ids are ranked by frequency over both sides: "a" (3 uses incl. duplicates) gets id 0
     assert pl.tok[pl.level_tok_off[0]] == 0
     # item_any = OR over the levels compare_terms can use (1..K-1, or 0 when K == 1)
@@ -148,7 +148,6 @@ def test_pack_hashed_signature_invariants():
     assert not p.exact_bits and p.n_vocab > 128
     sizes = p.level_sizes()
     n_head, n_tail_bits = np.bitwise_count(p.level_head), np.bitwise_count(p.level_tail)
-    assert np.array_equal(p.level_info >> 24, n_head)
     assert np.array_equal((p.level_info >> 16) & 0xFF, np.minimum(sizes - n_head - n_tail_bits, 255))
     assert np.array_equal(p.level_info & 0xFFFF, sizes)
     for g in range(p.n_levels):
