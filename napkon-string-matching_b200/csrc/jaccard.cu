@@ -21,11 +21,10 @@
 //   B  BOUND   (per step, integer + fp32 round-up, branch-free) exact head intersection by
 //              popcount plus an upper bound of the tail intersection from the signatures bounds
 //              every level score; compare_terms' weights are accumulated with directed rounding.
-//              The first four steps run as straight-line code, the rest in a loop that stops as
-//              soon as bound + remaining weight cannot reach the threshold.
+//              Six steps, straight-line; the weight of any later steps is granted in full.
 //   C  EXACT   per used level the exact |A & B| (popcount; only if both tail signatures collide,
-//              a merge over the tail ids), the reference's int/int float64 division and its
-//              accumulation order; score >= threshold in float64.
+//              a warp-cooperative intersection of the tail ids), the reference's int/int float64
+//              division and its accumulation order; score >= threshold in float64.
 // Kept pairs go to a per-warp staging buffer and are flushed with one global atomic per ~60
 // records as coalesced 16-byte stores.
 #include "nsm_common.cuh"
@@ -40,7 +39,9 @@ constexpr int J_GROUP = 16;      // left tiles per unit
 constexpr int J_RCP = 512;       // reciprocal table size
 constexpr int J_WARPS = JT_THREADS / 32;
 constexpr int J_OUT = 96;        // staged output records per warp
-constexpr int J_UNROLL = 4;      // steps of stage B that run as straight-line code
+constexpr int J_UNROLL = 6;      // steps of stage B, all straight-line code
+constexpr int J_AUNROLL = 4;     // left items per round of stage A
+constexpr int J_QA = 32 + 32 * J_AUNROLL;  // queue A capacity
 
 struct JaccardParams {
     nsm_sets_t L, R;
@@ -61,7 +62,7 @@ struct __align__(16) JaccardSmem {
     uint32_t l_k[JT_LEFT];
     uint32_t r_k[JT_THREADS];
     float rcp_up[J_RCP];
-    uint32_t qa[J_WARPS][64];
+    uint32_t qa[J_WARPS][J_QA];
     uint32_t qb[J_WARPS][64];
     unsigned long long stats[NSM_N_STATS];
 };
@@ -70,22 +71,42 @@ __device__ __forceinline__ float pow2_neg(uint32_t k) {  // 2^-k, 0 when it unde
     return k <= 126 ? __int_as_float((127 - (int)k) << 23) : 0.0f;
 }
 
-__device__ __forceinline__ uint32_t merge_count(const uint32_t *__restrict__ a, uint32_t na,
-                                                const uint32_t *__restrict__ b, uint32_t nb) {
+// |A & B| of two sorted id lists, computed by the whole warp (all arguments warp-uniform).
+// Small B (the usual case: a handful of tail ids): B lives in the lanes' registers and is
+// broadcast by shuffle against 32 ids of A at a time, so the only memory latency is one load of
+// each list.  Large B: every lane binary-searches its ids of A in B.
+__device__ __forceinline__ uint32_t warp_intersect_count(const uint32_t *__restrict__ a, uint32_t na,
+                                                         const uint32_t *__restrict__ b, uint32_t nb) {
     if (na == 0 || nb == 0) return 0;
-    uint32_t i = 0, j = 0, c = 0;
-    uint32_t x = __ldg(a), y = __ldg(b);
-    while (true) {
-        if (x == y) {
-            ++c; ++i; ++j;
-            if (i >= na || j >= nb) break;
-            x = __ldg(a + i); y = __ldg(b + j);
-        } else if (x < y) {
-            if (++i >= na) break;
-            x = __ldg(a + i);
-        } else {
-            if (++j >= nb) break;
-            y = __ldg(b + j);
+    if (na < nb) {
+        const uint32_t *tp = a; a = b; b = tp;
+        const uint32_t tn = na; na = nb; nb = tn;
+    }
+    const unsigned lane = lane_id();
+    uint32_t c = 0;
+    if (nb <= 32) {
+        const uint32_t yb = lane < nb ? __ldg(b + lane) : 0xffffffffu;
+        for (uint32_t base = 0; base < na; base += 32) {
+            const bool valid = base + lane < na;
+            const uint32_t x = valid ? __ldg(a + base + lane) : 0u;
+            bool hit = false;
+            for (uint32_t j = 0; j < nb; ++j) hit |= (x == __shfl_sync(FULL_MASK, yb, j));
+            c += __popc(__ballot_sync(FULL_MASK, hit && valid));
+        }
+    } else {
+        for (uint32_t base = 0; base < na; base += 32) {
+            const bool valid = base + lane < na;
+            bool hit = false;
+            if (valid) {
+                const uint32_t x = __ldg(a + base + lane);
+                uint32_t lo = 0, hi = nb;
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (__ldg(b + mid) < x) lo = mid + 1; else hi = mid;
+                }
+                hit = lo < nb && __ldg(b + lo) == x;
+            }
+            c += __popc(__ballot_sync(FULL_MASK, hit));
         }
     }
     return c;
@@ -198,6 +219,9 @@ jaccard_allpairs_kernel(const JaccardParams p) {
             const ulonglong2 any = __ldg(reinterpret_cast<const ulonglong2 *>(p.R.item_any) + r);
             rany_h = any.x; rany_t = any.y;
         }
+        // threshold <= 0 keeps every pair; an item without levels must reach stage C, which
+        // tells "both empty: score 0" from "one empty: IndexError upstream"
+        if (pass_all || kr == 0) rany_h = rany_t = ~0ull;
 
         const uint32_t lt_begin = lgroup * J_GROUP;
         const uint32_t lt_end = min(lt_begin + (uint32_t)J_GROUP, p.n_ltiles);
@@ -221,20 +245,22 @@ jaccard_allpairs_kernel(const JaccardParams p) {
             if (tid < nl) {
                 s.l_k[tid] = __ldg(p.L.item_k + l0 + tid);
                 s.l_cat[tid] = p.job.cat_mode ? __ldg(p.job.l_cat + l0 + tid) : 0;
-                if (p.any_depth == 0)
-                    s.l_any[tid] = __ldg(reinterpret_cast<const ulonglong2 *>(p.L.item_any) + l0 + tid);
             }
             __syncthreads();
-            if (p.any_depth != 0) {
-                if (tid < nl) {
-                    ulonglong2 any = make_ulonglong2(0, 0);
+            if (tid < nl) {
+                ulonglong2 any = make_ulonglong2(0, 0);
+                if (pass_all || s.l_k[tid] == 0) {
+                    any.x = any.y = ~0ull;
+                } else if (p.any_depth == 0) {
+                    any = __ldg(reinterpret_cast<const ulonglong2 *>(p.L.item_any) + l0 + tid);
+                } else {
                     for (uint32_t sl = 0; sl < min(p.any_depth, SL); ++sl) {
                         any.x |= s.l_ht[sl][tid].x; any.y |= s.l_ht[sl][tid].y;
                     }
-                    s.l_any[tid] = any;
                 }
-                __syncthreads();
+                s.l_any[tid] = any;
             }
+            __syncthreads();
 
             // The funnel as one loop, so that each stage's code exists once: fill queue A from
             // stage A until it holds a warp's worth (or the tile is exhausted), run stage B on 32
@@ -243,17 +269,26 @@ jaccard_allpairs_kernel(const JaccardParams p) {
             while (true) {
                 // ---- stage A: one left item x my right item -------------------------------
                 while (qa_n < 32 && li_next < nl) {
-                    const uint32_t li = li_next++;
-                    const ulonglong2 lany = s.l_any[li];
-                    bool pass = r_valid && keep_categories(p.job.cat_mode, s.l_cat[li], rcat);
-                    if (!pass_all) {
-                        const bool shared = ((lany.x & rany_h) | (lany.y & rany_t)) != 0;
-                        // an empty item against a non-empty one is an IndexError upstream
-                        pass = pass && (shared || ((s.l_k[li] == 0) != (kr == 0)));
+                    // four left items per round: four independent load -> test -> vote chains
+                    bool pass[J_AUNROLL];
+                    unsigned m[J_AUNROLL];
+#pragma unroll
+                    for (int u = 0; u < J_AUNROLL; ++u) {
+                        const uint32_t li = min(li_next + u, nl - 1);
+                        const ulonglong2 lany = s.l_any[li];
+                        pass[u] = r_valid && li_next + u < nl &&
+                                  ((lany.x & rany_h) | (lany.y & rany_t)) != 0;
+                        if (p.job.cat_mode)
+                            pass[u] = pass[u] && keep_categories(p.job.cat_mode, s.l_cat[li], rcat);
+                        m[u] = __ballot_sync(FULL_MASK, pass[u]);
                     }
-                    const unsigned m = __ballot_sync(FULL_MASK, pass);
-                    if (pass) s.qa[warp][qa_n + __popc(m & lanemask_lt())] = (li << 5) | lane;
-                    qa_n += __popc(m);
+#pragma unroll
+                    for (int u = 0; u < J_AUNROLL; ++u) {
+                        if (pass[u])
+                            s.qa[warp][qa_n + __popc(m[u] & lanemask_lt())] = ((li_next + u) << 5) | lane;
+                        qa_n += __popc(m[u]);
+                    }
+                    li_next += J_AUNROLL;
                 }
                 const bool tile_done = li_next >= nl;
                 if (qa_n == 0 && qb_n == 0 && tile_done) break;
@@ -284,24 +319,12 @@ jaccard_allpairs_kernel(const JaccardParams p) {
                             const float w = t <= kmax ? (flat ? 1.0f : pow2_neg(t)) : 0.0f;
                             ub = __fmaf_ru(__fmul_ru((float)ih, s.rcp_up[uh]), w, ub);
                         }
-                        if (kmax > (uint32_t)J_UNROLL) {
-                            const float w_last = pow2_neg(kmax);
-                            float w = pow2_neg(J_UNROLL);
-                            // weights still to come after step t: 2^-t - 2^-kmax
-                            pass = !(__fadd_ru(ub, __fsub_ru(w, w_last)) < p.thr_lo);
-                            for (uint32_t t = J_UNROLL + 1; pass && t <= kmax; ++t) {
-                                uint32_t ia, ib;
-                                const ulonglong2 A = left_level(li, l0 + li, t, kl, ia);
-                                const ulonglong2 B = right_level(rc, r0 + rc, t, c_kr, ib);
-                                const uint32_t ih = bound_intersection(A, ia, B, ib, exact_bits);
-                                const uint32_t uh = min((ia & 0xffffu) + (ib & 0xffffu) - ih,
-                                                        (uint32_t)J_RCP - 1);
-                                w = fmaxf(w * 0.5f, 1.17549435e-38f);
-                                ub = __fmaf_ru(__fmul_ru((float)ih, s.rcp_up[uh]), w, ub);
-                                pass = !(__fadd_ru(ub, __fsub_ru(w, w_last)) < p.thr_lo);
-                            }
-                        }
-                        pass = pass && ub >= p.thr_lo;
+                        // steps beyond the unrolled ones are not bounded individually: all their
+                        // weight, 2^-UNROLL - 2^-kmax, is granted (pairs this lets through are
+                        // within 2^-UNROLL of the threshold and get their exact score in stage C)
+                        if (kmax > (uint32_t)J_UNROLL)
+                            ub = __fadd_ru(ub, __fsub_ru(pow2_neg(J_UNROLL), pow2_neg(kmax)));
+                        pass = ub >= p.thr_lo;
                     }
                     const unsigned m = __ballot_sync(FULL_MASK, pass);
                     if (pass) s.qb[warp][qb_n + __popc(m & lanemask_lt())] = entry;
@@ -310,6 +333,8 @@ jaccard_allpairs_kernel(const JaccardParams p) {
                 }
 
                 // ---- stage C: exact score of one candidate per lane -----------------------
+                // The step loop is warp-uniform (lanes whose pair has fewer steps idle) so that
+                // the rare tail intersections can be computed by the whole warp.
                 if (qb_n >= 32 || (tile_done && qa_n == 0 && qb_n)) {
                     const uint32_t take = min(qb_n, 32u);
                     qb_n -= take;
@@ -317,55 +342,81 @@ jaccard_allpairs_kernel(const JaccardParams p) {
                     const uint32_t entry = active ? s.qb[warp][qb_n + lane] : 0u;
                     const uint32_t li = entry >> 5, rc = (warp << 5) | (entry & 31u);
                     const uint32_t c_l = l0 + li, c_r = r0 + rc;
-                    double score = 0.0;
+                    const uint32_t kl = s.l_k[li], c_kr = s.r_k[rc];
                     bool ok = active;
+                    uint32_t kmax = 0;
                     if (active) {
-                        const uint32_t kl = s.l_k[li], c_kr = s.r_k[rc];
                         ++st_cand;
                         if (kl == 0 || c_kr == 0) {
                             // both empty: compare_terms returns 0; one empty: IndexError upstream
                             if (kl != c_kr) { atomicOr(p.job.out_flags, NSM_FLAG_EMPTY_ITEM); ok = false; }
                         } else {
-                            const uint32_t kmax = flat ? 1u : max(kl, c_kr);
-                            double w = flat ? 2.0 : 1.0;
-                            uint32_t pjl = 0xffffffffu, pjr = 0xffffffffu, inter = 0, uni = 1;
-                            for (uint32_t t = 1; t <= kmax; ++t) {
-                                const uint32_t jl = flat ? 0u : min(t, kl - 1);
-                                const uint32_t jr = flat ? 0u : min(t, c_kr - 1);
-                                ++st_evals;
-                                if (jl != pjl || jr != pjr) {
-                                    pjl = jl; pjr = jr;
-                                    uint32_t ia, ib;
-                                    const ulonglong2 A = left_level(li, c_l, t, kl, ia);
-                                    const ulonglong2 B = right_level(rc, c_r, t, c_kr, ib);
-                                    const uint32_t a = ia & 0xffffu, b = ib & 0xffffu;
-                                    inter = __popcll(A.x & B.x);
-                                    const uint64_t tb = A.y & B.y;
-                                    if (tb) {
-                                        if (exact_bits) {
-                                            inter += __popcll(tb);
-                                        } else {
-                                            const uint32_t gl = __ldg(p.L.item_level_off + c_l) + jl;
-                                            const uint32_t gr = __ldg(p.R.item_level_off + c_r) + jr;
-                                            // a second, independent signature rules most collisions out
-                                            if (__ldg(p.L.level_tail2 + gl) & __ldg(p.R.level_tail2 + gr)) {
-                                                // ids are sorted: the tail ids follow the head ids
-                                                const uint32_t hl = __popcll(A.x), hr = __popcll(B.x);
-                                                inter += merge_count(
-                                                    p.L.tok + __ldg(p.L.level_tok_off + gl) + hl, a - hl,
-                                                    p.R.tok + __ldg(p.R.level_tok_off + gr) + hr, b - hr);
-                                                ++st_merges;
-                                            }
-                                        }
+                            kmax = flat ? 1u : max(kl, c_kr);
+                        }
+                    }
+                    // first level index of both items: only the tail-collision path needs them, but
+                    // fetching them now takes their latency off that path
+                    const uint32_t lg0 = exact_bits ? 0u : __ldg(p.L.item_level_off + c_l);
+                    const uint32_t rg0 = exact_bits ? 0u : __ldg(p.R.item_level_off + c_r);
+                    const uint32_t kmax_warp = __reduce_max_sync(FULL_MASK, kmax);
+                    double score = 0.0, w = flat ? 2.0 : 1.0;
+                    uint32_t pjl = 0xffffffffu, pjr = 0xffffffffu, inter = 0, uni = 1, a = 0, b = 0;
+                    for (uint32_t t = 1; t <= kmax_warp; ++t) {
+                        const bool on = t <= kmax;
+                        const uint32_t jl = flat ? 0u : min(t, kl - 1), jr = flat ? 0u : min(t, c_kr - 1);
+                        bool need = false;
+                        uint32_t hl = 0, hr = 0;
+                        if (on) {
+                            ++st_evals;
+                            if (jl != pjl || jr != pjr) {
+                                pjl = jl; pjr = jr;
+                                uint32_t ia, ib;
+                                const ulonglong2 A = left_level(li, c_l, t, kl, ia);
+                                const ulonglong2 B = right_level(rc, c_r, t, c_kr, ib);
+                                a = ia & 0xffffu; b = ib & 0xffffu;
+                                inter = __popcll(A.x & B.x);
+                                const uint64_t tb = A.y & B.y;
+                                if (tb) {
+                                    if (exact_bits) {
+                                        inter += __popcll(tb);
+                                    } else {  // ids are sorted: the tail ids follow the head ids
+                                        need = true; hl = __popcll(A.x); hr = __popcll(B.x);
                                     }
-                                    uni = a + b - inter;
                                 }
-                                w *= 0.5;
-                                // len(A & B) / len(A | B): int / int true division; score += s * w
-                                const double sc = __ddiv_rn((double)inter, (double)uni);
-                                if (uni == 0) { atomicOr(p.job.out_flags, NSM_FLAG_ZERO_UNION); ok = false; }
-                                score = __fma_rn(sc, w, score);
+                                uni = a + b - inter;
                             }
+                        }
+                        if (__any_sync(FULL_MASK, need)) {
+                            uint32_t off_a = 0, off_b = 0;
+                            if (need) {
+                                const uint32_t gl = lg0 + jl, gr = rg0 + jr;
+                                // a second, independent signature rules most collisions out
+                                if (__ldg(p.L.level_tail2 + gl) & __ldg(p.R.level_tail2 + gr)) {
+                                    off_a = __ldg(p.L.level_tok_off + gl) + hl;
+                                    off_b = __ldg(p.R.level_tok_off + gr) + hr;
+                                } else {
+                                    need = false;
+                                }
+                            }
+                            unsigned todo = __ballot_sync(FULL_MASK, need);
+                            while (todo) {
+                                const int src = __ffs(todo) - 1;
+                                todo &= todo - 1;
+                                const uint32_t c = warp_intersect_count(
+                                    p.L.tok + __shfl_sync(FULL_MASK, off_a, src), __shfl_sync(FULL_MASK, a - hl, src),
+                                    p.R.tok + __shfl_sync(FULL_MASK, off_b, src), __shfl_sync(FULL_MASK, b - hr, src));
+                                if ((int)lane == src) { inter += c; uni = a + b - inter; ++st_merges; }
+                            }
+                        }
+                        if (on) {
+                            w *= 0.5;
+                            if (inter) {
+                                // len(A & B) / len(A | B): int / int true division; score += s * w
+                                score = __fma_rn(__ddiv_rn((double)inter, (double)uni), w, score);
+                            } else if (uni == 0) {  // 0 / 0: ZeroDivisionError upstream
+                                atomicOr(p.job.out_flags, NSM_FLAG_ZERO_UNION);
+                                ok = false;
+                            }  // else 0 / uni = +0.0 and score + 0.0 * w == score
                         }
                     }
                     // ---- threshold compaction into the warp's staging buffer ---------------
