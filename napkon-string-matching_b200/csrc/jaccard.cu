@@ -9,12 +9,13 @@
 // are also laid out by compare_terms' step ("slot" t-1 holds level min(t, K-1) of each item),
 // slot-major, so that the data of a block of consecutive items is contiguous per step.
 //
-// Work decomposition: a unit is one block of JT_THREADS right items x a group of left tiles of
-// JT_LEFT items.  The right block's slots are staged once per unit in shared memory, one column
-// per thread (lane i reads word i: conflict-free); the left tile's slots likewise.  Each warp
-// runs a three-stage funnel over its 32 right items x the tile's left items, re-compacting the
-// survivors of every stage through a per-warp shared-memory queue (ballot + popc) so that each
-// stage runs with 32 busy lanes:
+// Work decomposition: a unit is one block of JT_THREADS right items x J_UNIT_LEFT left items.
+// The right block's slots are staged once per unit in shared memory, one column per thread
+// (lane i reads word i: conflict-free), together with one 128-bit "any" word per left item; the
+// left items' slots are read through L1 where a pair needs them.  Each warp then runs a
+// three-stage funnel over its 32 right items x the unit's left items with no block-wide barrier,
+// re-compacting the survivors of every stage through a per-warp shared-memory queue (ballot +
+// popc) so that each stage runs with 32 busy lanes:
 //   A  ANY     (per item pair, ~8 integer ops) the OR of the summaries over the first D steps
 //              (2^-D < threshold: later steps cannot lift a zero score over the threshold) shares
 //              no bit => no level pair that matters shares a token => pair proven < threshold.
@@ -25,22 +26,21 @@
 //   C  EXACT   per used level the exact |A & B| (popcount; only if both tail signatures collide,
 //              a warp-cooperative intersection of the tail ids), the reference's int/int float64
 //              division and its accumulation order; score >= threshold in float64.
-// Kept pairs go to a per-warp staging buffer and are flushed with one global atomic per ~60
+// Kept pairs go to a per-warp staging buffer and are flushed with one global atomic per ~50
 // records as coalesced 16-byte stores.
 #include "nsm_common.cuh"
 
 namespace nsm {
 
-constexpr int JT_THREADS = 128;  // right items per block (= threads per CTA)
-constexpr int JT_CTAS = 4;       // resident CTAs per SM the kernel is sized for
-constexpr int JT_LEFT = 64;      // left items per tile
-constexpr int J_SLOTS = 10;      // steps staged per item (pack.py SLOT_CAP)
-constexpr int J_GROUP = 16;      // left tiles per unit
-constexpr int J_RCP = 512;       // reciprocal table size
+constexpr int JT_THREADS = 128;   // right items per block (= threads per CTA)
+constexpr int JT_CTAS = 5;        // resident CTAs per SM the kernel is sized for
+constexpr int J_UNIT_LEFT = 512;  // left items per unit
+constexpr int J_SLOTS = 10;       // steps staged per item (pack.py SLOT_CAP)
+constexpr int J_RCP = 512;        // reciprocal table size
 constexpr int J_WARPS = JT_THREADS / 32;
-constexpr int J_OUT = 96;        // staged output records per warp
-constexpr int J_UNROLL = 6;      // steps of stage B, all straight-line code
-constexpr int J_AUNROLL = 4;     // left items per round of stage A
+constexpr int J_OUT = 64;         // staged output records per warp
+constexpr int J_UNROLL = 6;       // steps of stage B, all straight-line code
+constexpr int J_AUNROLL = 4;      // left items per round of stage A
 constexpr int J_QA = 32 + 32 * J_AUNROLL;  // queue A capacity
 
 struct JaccardParams {
@@ -48,22 +48,19 @@ struct JaccardParams {
     nsm_job_t job;
     float thr_lo;        // filter threshold (see filter_threshold); -inf: everything passes
     uint32_t any_depth;  // D of stage A; 0: use the packed all-level item_any
-    uint32_t n_ltiles, n_lgroups, n_rblocks;
+    uint32_t n_lchunks, n_rblocks;
 };
 
 struct __align__(16) JaccardSmem {
-    ulonglong2 l_ht[J_SLOTS][JT_LEFT];  // (head, tail)
-    ulonglong2 r_ht[J_SLOTS][JT_THREADS];
-    ulonglong2 l_any[JT_LEFT];
+    ulonglong2 r_ht[J_SLOTS][JT_THREADS];  // (head, tail) per step of my right block
+    ulonglong2 l_any[J_UNIT_LEFT];         // stage A word of every left item of the unit
     nsm_pair_t out[J_WARPS][J_OUT];
-    uint64_t l_cat[JT_LEFT];
-    uint32_t l_info[J_SLOTS][JT_LEFT];  // size | fold count << 16
-    uint32_t r_info[J_SLOTS][JT_THREADS];
-    uint32_t l_k[JT_LEFT];
+    uint32_t r_info[J_SLOTS][JT_THREADS];  // size | fold count << 16
     uint32_t r_k[JT_THREADS];
     float rcp_up[J_RCP];
     uint32_t qa[J_WARPS][J_QA];
     uint32_t qb[J_WARPS][64];
+    uint16_t l_k[J_UNIT_LEFT];
     unsigned long long stats[NSM_N_STATS];
 };
 
@@ -138,6 +135,7 @@ jaccard_allpairs_kernel(const JaccardParams p) {
     const double thr = p.job.threshold;
     const bool pass_all = !(p.thr_lo > -INFINITY) && !(p.thr_lo != p.thr_lo);  // thr <= 0
     const uint32_t SL = p.L.n_slots, SR = p.R.n_slots;
+    const ulonglong2 *l_slot_ht = reinterpret_cast<const ulonglong2 *>(p.L.slot_ht);
 
     for (unsigned u = tid; u < J_RCP; u += JT_THREADS) s.rcp_up[u] = u ? __frcp_ru((float)u) : 0.0f;
     if (tid < NSM_N_STATS) s.stats[tid] = 0;
@@ -161,17 +159,17 @@ jaccard_allpairs_kernel(const JaccardParams p) {
         out_n = 0;
     };
 
-    // summary of item `col` of the staged tile/block at step t >= 1 (CSR arrays when the item
-    // has more levels than slots and t lies beyond them)
-    auto left_level = [&](uint32_t li, uint32_t item, uint32_t t, uint32_t k, uint32_t &info) {
+    // summary of one item at step t >= 1: from the slot arrays, or from the CSR arrays when the
+    // item has more levels than slots and t lies beyond them
+    auto left_level = [&](uint32_t item, uint32_t t, uint32_t k, uint32_t &info) {
         if (DEEP && t > SL && k > SL + 1) {
             const uint32_t g = __ldg(p.L.item_level_off + item) + min(t, k - 1);
             info = __ldg(p.L.level_info + g);
             return make_ulonglong2(__ldg(p.L.level_head + g), __ldg(p.L.level_tail + g));
         }
-        const uint32_t sl = min(t, SL) - 1;
-        info = s.l_info[sl][li];
-        return s.l_ht[sl][li];
+        const size_t at = (size_t)(min(t, SL) - 1) * p.L.n_items + item;
+        info = __ldg(p.L.slot_info + at);
+        return __ldg(l_slot_ht + at);
     };
     auto right_level = [&](uint32_t rc, uint32_t item, uint32_t t, uint32_t k, uint32_t &info) {
         if (DEEP && t > SR && k > SR + 1) {
@@ -184,10 +182,12 @@ jaccard_allpairs_kernel(const JaccardParams p) {
         return s.r_ht[sr][rc];
     };
 
-    const uint32_t n_units = p.n_lgroups * p.n_rblocks;
+    const uint32_t n_units = p.n_lchunks * p.n_rblocks;
     for (uint32_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-        const uint32_t rb = unit / p.n_lgroups, lgroup = unit - rb * p.n_lgroups;
+        const uint32_t rb = unit / p.n_lchunks, lchunk = unit - rb * p.n_lchunks;
         const uint32_t r0 = rb * JT_THREADS;
+        const uint32_t l0 = p.job.l_row_begin + lchunk * J_UNIT_LEFT;
+        const uint32_t nl = min((uint32_t)J_UNIT_LEFT, p.job.l_row_end - l0);
 
         __syncthreads();  // previous unit fully consumed
         // ---- stage my right item's slots: one column per thread ---------------------------
@@ -222,219 +222,198 @@ jaccard_allpairs_kernel(const JaccardParams p) {
         // threshold <= 0 keeps every pair; an item without levels must reach stage C, which
         // tells "both empty: score 0" from "one empty: IndexError upstream"
         if (pass_all || kr == 0) rany_h = rany_t = ~0ull;
-
-        const uint32_t lt_begin = lgroup * J_GROUP;
-        const uint32_t lt_end = min(lt_begin + (uint32_t)J_GROUP, p.n_ltiles);
-        for (uint32_t lt = lt_begin; lt < lt_end; ++lt) {
-            const uint32_t l0 = p.job.l_row_begin + lt * JT_LEFT;
-            const uint32_t nl = min((uint32_t)JT_LEFT, p.job.l_row_end - l0);
-
-            __syncthreads();  // previous tile consumed (and the right block staged)
-            for (uint32_t e = tid; e < SL * JT_LEFT; e += JT_THREADS) {
-                const uint32_t sl = e / JT_LEFT, li = e % JT_LEFT;
-                ulonglong2 ht = make_ulonglong2(0, 0);
-                uint32_t inf = 0;
-                if (li < nl) {
-                    const size_t at = (size_t)sl * p.L.n_items + l0 + li;
-                    ht = __ldg(reinterpret_cast<const ulonglong2 *>(p.L.slot_ht) + at);
-                    inf = __ldg(p.L.slot_info + at);
+        // ---- the unit's left items: stage A word and level count -------------------------
+        for (uint32_t li = tid; li < nl; li += JT_THREADS) {
+            const uint32_t k = __ldg(p.L.item_k + l0 + li);
+            ulonglong2 any = make_ulonglong2(0, 0);
+            if (pass_all || k == 0) {
+                any.x = any.y = ~0ull;
+            } else if (p.any_depth == 0) {
+                any = __ldg(reinterpret_cast<const ulonglong2 *>(p.L.item_any) + l0 + li);
+            } else {
+                for (uint32_t sl = 0; sl < min(p.any_depth, SL); ++sl) {
+                    const ulonglong2 ht = __ldg(l_slot_ht + (size_t)sl * p.L.n_items + l0 + li);
+                    any.x |= ht.x; any.y |= ht.y;
                 }
-                s.l_ht[sl][li] = ht;
-                s.l_info[sl][li] = inf;
             }
-            if (tid < nl) {
-                s.l_k[tid] = __ldg(p.L.item_k + l0 + tid);
-                s.l_cat[tid] = p.job.cat_mode ? __ldg(p.job.l_cat + l0 + tid) : 0;
-            }
-            __syncthreads();
-            if (tid < nl) {
-                ulonglong2 any = make_ulonglong2(0, 0);
-                if (pass_all || s.l_k[tid] == 0) {
-                    any.x = any.y = ~0ull;
-                } else if (p.any_depth == 0) {
-                    any = __ldg(reinterpret_cast<const ulonglong2 *>(p.L.item_any) + l0 + tid);
-                } else {
-                    for (uint32_t sl = 0; sl < min(p.any_depth, SL); ++sl) {
-                        any.x |= s.l_ht[sl][tid].x; any.y |= s.l_ht[sl][tid].y;
-                    }
-                }
-                s.l_any[tid] = any;
-            }
-            __syncthreads();
+            s.l_any[li] = any;
+            s.l_k[li] = (uint16_t)min(k, 0xffffu);
+        }
+        __syncthreads();
 
-            // The funnel as one loop, so that each stage's code exists once: fill queue A from
-            // stage A until it holds a warp's worth (or the tile is exhausted), run stage B on 32
-            // entries, run stage C whenever queue B holds 32 (or everything before it is done).
-            uint32_t qa_n = 0, qb_n = 0, li_next = 0;  // warp-uniform
-            while (true) {
-                // ---- stage A: one left item x my right item -------------------------------
-                while (qa_n < 32 && li_next < nl) {
-                    // four left items per round: four independent load -> test -> vote chains
-                    bool pass[J_AUNROLL];
-                    unsigned m[J_AUNROLL];
+        // The funnel as one loop, so that each stage's code exists once: fill queue A from stage
+        // A until it holds a warp's worth (or the unit is exhausted), run stage B on 32 entries,
+        // run stage C whenever queue B holds 32 (or everything before it is done).
+        uint32_t qa_n = 0, qb_n = 0, li_next = 0;  // warp-uniform
+        while (true) {
+            // ---- stage A: left items x my right item ----------------------------------------
+            while (qa_n < 32 && li_next < nl) {
+                // four left items per round: four independent load -> test -> vote chains
+                bool pass[J_AUNROLL];
+                unsigned m[J_AUNROLL];
 #pragma unroll
-                    for (int u = 0; u < J_AUNROLL; ++u) {
-                        const uint32_t li = min(li_next + u, nl - 1);
-                        const ulonglong2 lany = s.l_any[li];
-                        pass[u] = r_valid && li_next + u < nl &&
-                                  ((lany.x & rany_h) | (lany.y & rany_t)) != 0;
-                        if (p.job.cat_mode)
-                            pass[u] = pass[u] && keep_categories(p.job.cat_mode, s.l_cat[li], rcat);
-                        m[u] = __ballot_sync(FULL_MASK, pass[u]);
-                    }
-#pragma unroll
-                    for (int u = 0; u < J_AUNROLL; ++u) {
-                        if (pass[u])
-                            s.qa[warp][qa_n + __popc(m[u] & lanemask_lt())] = ((li_next + u) << 5) | lane;
-                        qa_n += __popc(m[u]);
-                    }
-                    li_next += J_AUNROLL;
+                for (int u = 0; u < J_AUNROLL; ++u) {
+                    const uint32_t li = min(li_next + u, nl - 1);
+                    const ulonglong2 lany = s.l_any[li];
+                    pass[u] = r_valid && li_next + u < nl &&
+                              ((lany.x & rany_h) | (lany.y & rany_t)) != 0;
+                    if (p.job.cat_mode)
+                        pass[u] = pass[u] && keep_categories(p.job.cat_mode, __ldg(p.job.l_cat + l0 + li), rcat);
+                    m[u] = __ballot_sync(FULL_MASK, pass[u]);
                 }
-                const bool tile_done = li_next >= nl;
-                if (qa_n == 0 && qb_n == 0 && tile_done) break;
+#pragma unroll
+                for (int u = 0; u < J_AUNROLL; ++u) {
+                    if (pass[u])
+                        s.qa[warp][qa_n + __popc(m[u] & lanemask_lt())] = ((li_next + u) << 5) | lane;
+                    qa_n += __popc(m[u]);
+                }
+                li_next += J_AUNROLL;
+            }
+            const bool unit_done = li_next >= nl;
+            if (qa_n == 0 && qb_n == 0 && unit_done) break;
+            __syncwarp();
+
+            // ---- stage B: fp32 upper bound of one surviving pair per lane -----------------
+            if (qa_n >= 32 || (unit_done && qa_n)) {
+                const uint32_t take = min(qa_n, 32u);
+                qa_n -= take;
+                const bool active = lane < take;
+                const uint32_t entry = active ? s.qa[warp][qa_n + lane] : 0u;
+                const uint32_t li = entry >> 5, rc = (warp << 5) | (entry & 31u);
+                const uint32_t kl = s.l_k[li], c_kr = s.r_k[rc];
+                bool pass = active;
+                if (active && !pass_all && kl != 0 && c_kr != 0) {
+                    const uint32_t kmax = flat ? 1u : max(kl, c_kr);
+                    float ub = 0.0f;
+                    ++st_bound;
+#pragma unroll
+                    for (uint32_t t = 1; t <= (uint32_t)J_UNROLL; ++t) {
+                        // steps beyond kmax read a repeated level and get weight 0
+                        const uint32_t sr = min(t, SR) - 1;
+                        const size_t at = (size_t)(min(t, SL) - 1) * p.L.n_items + l0 + li;
+                        const uint32_t ia = __ldg(p.L.slot_info + at), ib = s.r_info[sr][rc];
+                        const uint32_t ih = bound_intersection(__ldg(l_slot_ht + at), ia, s.r_ht[sr][rc],
+                                                               ib, exact_bits);
+                        const uint32_t uh = min((ia & 0xffffu) + (ib & 0xffffu) - ih,
+                                                (uint32_t)J_RCP - 1);  // 1/511 >= 1/u beyond
+                        const float w = t <= kmax ? (flat ? 1.0f : pow2_neg(t)) : 0.0f;
+                        ub = __fmaf_ru(__fmul_ru((float)ih, s.rcp_up[uh]), w, ub);
+                    }
+                    // steps beyond the unrolled ones are not bounded individually: all their
+                    // weight, 2^-UNROLL - 2^-kmax, is granted (pairs this lets through are within
+                    // 2^-UNROLL of the threshold and get their exact score in stage C)
+                    if (kmax > (uint32_t)J_UNROLL)
+                        ub = __fadd_ru(ub, __fsub_ru(pow2_neg(J_UNROLL), pow2_neg(kmax)));
+                    pass = ub >= p.thr_lo;
+                }
+                const unsigned m = __ballot_sync(FULL_MASK, pass);
+                if (pass) s.qb[warp][qb_n + __popc(m & lanemask_lt())] = entry;
+                qb_n += __popc(m);
                 __syncwarp();
+            }
 
-                // ---- stage B: fp32 upper bound of one surviving pair per lane -------------
-                if (qa_n >= 32 || (tile_done && qa_n)) {
-                    const uint32_t take = min(qa_n, 32u);
-                    qa_n -= take;
-                    const bool active = lane < take;
-                    const uint32_t entry = active ? s.qa[warp][qa_n + lane] : 0u;
-                    const uint32_t li = entry >> 5, rc = (warp << 5) | (entry & 31u);
-                    const uint32_t kl = s.l_k[li], c_kr = s.r_k[rc];
-                    bool pass = active;
-                    if (active && !pass_all && kl != 0 && c_kr != 0) {
-                        const uint32_t kmax = flat ? 1u : max(kl, c_kr);
-                        float ub = 0.0f;
-                        ++st_bound;
-#pragma unroll
-                        for (uint32_t t = 1; t <= (uint32_t)J_UNROLL; ++t) {
-                            // steps beyond kmax read a repeated level and get weight 0
-                            const uint32_t sl = min(t, SL) - 1, sr = min(t, SR) - 1;
-                            const uint32_t ia = s.l_info[sl][li], ib = s.r_info[sr][rc];
-                            const uint32_t ih = bound_intersection(s.l_ht[sl][li], ia, s.r_ht[sr][rc],
-                                                                   ib, exact_bits);
-                            const uint32_t uh = min((ia & 0xffffu) + (ib & 0xffffu) - ih,
-                                                    (uint32_t)J_RCP - 1);  // 1/511 >= 1/u beyond
-                            const float w = t <= kmax ? (flat ? 1.0f : pow2_neg(t)) : 0.0f;
-                            ub = __fmaf_ru(__fmul_ru((float)ih, s.rcp_up[uh]), w, ub);
-                        }
-                        // steps beyond the unrolled ones are not bounded individually: all their
-                        // weight, 2^-UNROLL - 2^-kmax, is granted (pairs this lets through are
-                        // within 2^-UNROLL of the threshold and get their exact score in stage C)
-                        if (kmax > (uint32_t)J_UNROLL)
-                            ub = __fadd_ru(ub, __fsub_ru(pow2_neg(J_UNROLL), pow2_neg(kmax)));
-                        pass = ub >= p.thr_lo;
+            // ---- stage C: exact score of one candidate per lane ---------------------------
+            // The step loop is warp-uniform (lanes whose pair has fewer steps idle) so that the
+            // rare tail intersections can be computed by the whole warp.
+            if (qb_n >= 32 || (unit_done && qa_n == 0 && qb_n)) {
+                const uint32_t take = min(qb_n, 32u);
+                qb_n -= take;
+                const bool active = lane < take;
+                const uint32_t entry = active ? s.qb[warp][qb_n + lane] : 0u;
+                const uint32_t li = entry >> 5, rc = (warp << 5) | (entry & 31u);
+                const uint32_t c_l = l0 + li, c_r = r0 + rc;
+                const uint32_t kl = s.l_k[li], c_kr = s.r_k[rc];
+                bool ok = active;
+                uint32_t kmax = 0;
+                if (active) {
+                    ++st_cand;
+                    if (kl == 0 || c_kr == 0) {
+                        // both empty: compare_terms returns 0; one empty: IndexError upstream
+                        if (kl != c_kr) { atomicOr(p.job.out_flags, NSM_FLAG_EMPTY_ITEM); ok = false; }
+                    } else {
+                        kmax = flat ? 1u : max(kl, c_kr);
                     }
-                    const unsigned m = __ballot_sync(FULL_MASK, pass);
-                    if (pass) s.qb[warp][qb_n + __popc(m & lanemask_lt())] = entry;
-                    qb_n += __popc(m);
-                    __syncwarp();
                 }
-
-                // ---- stage C: exact score of one candidate per lane -----------------------
-                // The step loop is warp-uniform (lanes whose pair has fewer steps idle) so that
-                // the rare tail intersections can be computed by the whole warp.
-                if (qb_n >= 32 || (tile_done && qa_n == 0 && qb_n)) {
-                    const uint32_t take = min(qb_n, 32u);
-                    qb_n -= take;
-                    const bool active = lane < take;
-                    const uint32_t entry = active ? s.qb[warp][qb_n + lane] : 0u;
-                    const uint32_t li = entry >> 5, rc = (warp << 5) | (entry & 31u);
-                    const uint32_t c_l = l0 + li, c_r = r0 + rc;
-                    const uint32_t kl = s.l_k[li], c_kr = s.r_k[rc];
-                    bool ok = active;
-                    uint32_t kmax = 0;
-                    if (active) {
-                        ++st_cand;
-                        if (kl == 0 || c_kr == 0) {
-                            // both empty: compare_terms returns 0; one empty: IndexError upstream
-                            if (kl != c_kr) { atomicOr(p.job.out_flags, NSM_FLAG_EMPTY_ITEM); ok = false; }
-                        } else {
-                            kmax = flat ? 1u : max(kl, c_kr);
-                        }
-                    }
-                    // first level index of both items: only the tail-collision path needs them, but
-                    // fetching them now takes their latency off that path
-                    const uint32_t lg0 = exact_bits ? 0u : __ldg(p.L.item_level_off + c_l);
-                    const uint32_t rg0 = exact_bits ? 0u : __ldg(p.R.item_level_off + c_r);
-                    const uint32_t kmax_warp = __reduce_max_sync(FULL_MASK, kmax);
-                    double score = 0.0, w = flat ? 2.0 : 1.0;
-                    uint32_t pjl = 0xffffffffu, pjr = 0xffffffffu, inter = 0, uni = 1, a = 0, b = 0;
-                    for (uint32_t t = 1; t <= kmax_warp; ++t) {
-                        const bool on = t <= kmax;
-                        const uint32_t jl = flat ? 0u : min(t, kl - 1), jr = flat ? 0u : min(t, c_kr - 1);
-                        bool need = false;
-                        uint32_t hl = 0, hr = 0;
-                        if (on) {
-                            ++st_evals;
-                            if (jl != pjl || jr != pjr) {
-                                pjl = jl; pjr = jr;
-                                uint32_t ia, ib;
-                                const ulonglong2 A = left_level(li, c_l, t, kl, ia);
-                                const ulonglong2 B = right_level(rc, c_r, t, c_kr, ib);
-                                a = ia & 0xffffu; b = ib & 0xffffu;
-                                inter = __popcll(A.x & B.x);
-                                const uint64_t tb = A.y & B.y;
-                                if (tb) {
-                                    if (exact_bits) {
-                                        inter += __popcll(tb);
-                                    } else {  // ids are sorted: the tail ids follow the head ids
-                                        need = true; hl = __popcll(A.x); hr = __popcll(B.x);
-                                    }
-                                }
-                                uni = a + b - inter;
-                            }
-                        }
-                        if (__any_sync(FULL_MASK, need)) {
-                            uint32_t off_a = 0, off_b = 0;
-                            if (need) {
-                                const uint32_t gl = lg0 + jl, gr = rg0 + jr;
-                                // a second, independent signature rules most collisions out
-                                if (__ldg(p.L.level_tail2 + gl) & __ldg(p.R.level_tail2 + gr)) {
-                                    off_a = __ldg(p.L.level_tok_off + gl) + hl;
-                                    off_b = __ldg(p.R.level_tok_off + gr) + hr;
-                                } else {
-                                    need = false;
+                // first level index of both items: only the tail-collision path needs them, but
+                // fetching them now takes their latency off that path
+                const uint32_t lg0 = exact_bits ? 0u : __ldg(p.L.item_level_off + c_l);
+                const uint32_t rg0 = exact_bits ? 0u : __ldg(p.R.item_level_off + c_r);
+                const uint32_t kmax_warp = __reduce_max_sync(FULL_MASK, kmax);
+                double score = 0.0, w = flat ? 2.0 : 1.0;
+                uint32_t pjl = 0xffffffffu, pjr = 0xffffffffu, inter = 0, uni = 1, a = 0, b = 0;
+                for (uint32_t t = 1; t <= kmax_warp; ++t) {
+                    const bool on = t <= kmax;
+                    const uint32_t jl = flat ? 0u : min(t, kl - 1), jr = flat ? 0u : min(t, c_kr - 1);
+                    bool need = false;
+                    uint32_t hl = 0, hr = 0;
+                    if (on) {
+                        ++st_evals;
+                        if (jl != pjl || jr != pjr) {
+                            pjl = jl; pjr = jr;
+                            uint32_t ia, ib;
+                            const ulonglong2 A = left_level(c_l, t, kl, ia);
+                            const ulonglong2 B = right_level(rc, c_r, t, c_kr, ib);
+                            a = ia & 0xffffu; b = ib & 0xffffu;
+                            inter = __popcll(A.x & B.x);
+                            const uint64_t tb = A.y & B.y;
+                            if (tb) {
+                                if (exact_bits) {
+                                    inter += __popcll(tb);
+                                } else {  // ids are sorted: the tail ids follow the head ids
+                                    need = true; hl = __popcll(A.x); hr = __popcll(B.x);
                                 }
                             }
-                            unsigned todo = __ballot_sync(FULL_MASK, need);
-                            while (todo) {
-                                const int src = __ffs(todo) - 1;
-                                todo &= todo - 1;
-                                const uint32_t c = warp_intersect_count(
-                                    p.L.tok + __shfl_sync(FULL_MASK, off_a, src), __shfl_sync(FULL_MASK, a - hl, src),
-                                    p.R.tok + __shfl_sync(FULL_MASK, off_b, src), __shfl_sync(FULL_MASK, b - hr, src));
-                                if ((int)lane == src) { inter += c; uni = a + b - inter; ++st_merges; }
+                            uni = a + b - inter;
+                        }
+                    }
+                    if (__any_sync(FULL_MASK, need)) {
+                        uint32_t off_a = 0, off_b = 0;
+                        if (need) {
+                            const uint32_t gl = lg0 + jl, gr = rg0 + jr;
+                            // a second, independent signature rules most collisions out
+                            if (__ldg(p.L.level_tail2 + gl) & __ldg(p.R.level_tail2 + gr)) {
+                                off_a = __ldg(p.L.level_tok_off + gl) + hl;
+                                off_b = __ldg(p.R.level_tok_off + gr) + hr;
+                            } else {
+                                need = false;
                             }
                         }
-                        if (on) {
-                            w *= 0.5;
-                            if (inter) {
-                                // len(A & B) / len(A | B): int / int true division; score += s * w
-                                score = __fma_rn(__ddiv_rn((double)inter, (double)uni), w, score);
-                            } else if (uni == 0) {  // 0 / 0: ZeroDivisionError upstream
-                                atomicOr(p.job.out_flags, NSM_FLAG_ZERO_UNION);
-                                ok = false;
-                            }  // else 0 / uni = +0.0 and score + 0.0 * w == score
+                        unsigned todo = __ballot_sync(FULL_MASK, need);
+                        while (todo) {
+                            const int src = __ffs(todo) - 1;
+                            todo &= todo - 1;
+                            const uint32_t c = warp_intersect_count(
+                                p.L.tok + __shfl_sync(FULL_MASK, off_a, src), __shfl_sync(FULL_MASK, a - hl, src),
+                                p.R.tok + __shfl_sync(FULL_MASK, off_b, src), __shfl_sync(FULL_MASK, b - hr, src));
+                            if ((int)lane == src) { inter += c; uni = a + b - inter; ++st_merges; }
                         }
                     }
-                    // ---- threshold compaction into the warp's staging buffer ---------------
-                    const bool keep = ok && score >= thr;
-                    const unsigned m = __ballot_sync(FULL_MASK, keep);
-                    if (m) {
-                        const uint32_t n = __popc(m);
-                        if (out_n + n > J_OUT) flush_out();
-                        if (keep) {
-                            double2 rec;
-                            rec.x = __longlong_as_double((long long)(((unsigned long long)c_r << 32) | c_l));
-                            rec.y = score;
-                            reinterpret_cast<double2 *>(&s.out[warp][0])[out_n + __popc(m & lanemask_lt())] = rec;
-                        }
-                        out_n += n;
+                    if (on) {
+                        w *= 0.5;
+                        if (inter) {
+                            // len(A & B) / len(A | B): int / int true division; score += s * w
+                            score = __fma_rn(__ddiv_rn((double)inter, (double)uni), w, score);
+                        } else if (uni == 0) {  // 0 / 0: ZeroDivisionError upstream
+                            atomicOr(p.job.out_flags, NSM_FLAG_ZERO_UNION);
+                            ok = false;
+                        }  // else 0 / uni = +0.0 and score + 0.0 * w == score
                     }
-                    __syncwarp();
                 }
+                // ---- threshold compaction into the warp's staging buffer -------------------
+                const bool keep = ok && score >= thr;
+                const unsigned m = __ballot_sync(FULL_MASK, keep);
+                if (m) {
+                    const uint32_t n = __popc(m);
+                    if (out_n + n > J_OUT) flush_out();
+                    if (keep) {
+                        double2 rec;
+                        rec.x = __longlong_as_double((long long)(((unsigned long long)c_r << 32) | c_l));
+                        rec.y = score;
+                        reinterpret_cast<double2 *>(&s.out[warp][0])[out_n + __popc(m & lanemask_lt())] = rec;
+                    }
+                    out_n += n;
+                }
+                __syncwarp();
             }
         }
     }
@@ -476,6 +455,10 @@ extern "C" int nsm_jaccard_allpairs(const nsm_sets_t *left, const nsm_sets_t *ri
         set_error("flat scoring needs items with exactly one level");
         return NSM_ERR_BAD_ARG;
     }
+    if (left->max_levels > 0xffffu || right->max_levels > 0xffffu) {
+        set_error("items with more than 65535 levels are not supported");
+        return NSM_ERR_UNSUPPORTED;
+    }
     if (left->n_slots < 1 || left->n_slots > (uint32_t)J_SLOTS || right->n_slots < 1 ||
         right->n_slots > (uint32_t)J_SLOTS) {
         set_error("n_slots must be in 1..%d", J_SLOTS);
@@ -498,10 +481,9 @@ extern "C" int nsm_jaccard_allpairs(const nsm_sets_t *left, const nsm_sets_t *ri
             p.any_depth = d < (uint32_t)J_SLOTS ? d : (uint32_t)J_SLOTS;
     }
     const uint32_t n_rows = job->l_row_end - job->l_row_begin;
-    p.n_ltiles = (n_rows + JT_LEFT - 1) / JT_LEFT;
-    p.n_lgroups = (p.n_ltiles + J_GROUP - 1) / J_GROUP;
+    p.n_lchunks = (n_rows + J_UNIT_LEFT - 1) / J_UNIT_LEFT;
     p.n_rblocks = (right->n_items + JT_THREADS - 1) / JT_THREADS;
-    const uint64_t n_units = (uint64_t)p.n_lgroups * p.n_rblocks;
+    const uint64_t n_units = (uint64_t)p.n_lchunks * p.n_rblocks;
     if (n_units > 0xffffffffull) {
         set_error("too many work units (%llu); split the left row block", (unsigned long long)n_units);
         return NSM_ERR_UNSUPPORTED;
