@@ -40,6 +40,19 @@ class DeviceCohort:
     weights: np.ndarray             # per-item work estimate, for row-block balancing
 
 
+@dataclass
+class Job:
+    """One all-pairs comparison: left[rows] x right, keep score >= threshold."""
+    left: DeviceCohort
+    right: DeviceCohort
+    threshold: float
+    flat: bool = False
+    rows: Optional[Tuple[int, int]] = None
+    l_cat: Optional[torch.Tensor] = None
+    r_cat: Optional[torch.Tensor] = None
+    cat_mode: int = nsmlib.CAT_OFF
+
+
 class Engine:
     def __init__(self, device: Optional[int] = None, max_pairs_per_block: int = 1 << 30):
         _require_cuda()
@@ -51,6 +64,9 @@ class Engine:
         self.time_kernels = False   # bracket every comparison kernel with CUDA events
         self.kernel_ms = 0.0
         self.kernel_launches_timed = 0
+        self._timed: List[Tuple[torch.cuda.Event, torch.cuda.Event]] = []
+        self._copy_stream: Optional[torch.cuda.Stream] = None
+        self.last_infos: List[Dict] = []
         self.last_info: Dict = {}
 
     # ------------------------------------------------------------------ uploads
@@ -128,76 +144,119 @@ class Engine:
                   cat_mode: int = nsmlib.CAT_OFF, capacity: Optional[int] = None,
                   to_host: bool = True, copy: bool = True) -> np.ndarray:
         """Scores left[rows] x right and returns the kept records (``PAIR_DTYPE``), in no
-        particular order.
+        particular order.  See :meth:`run_jobs`; counters are in ``self.last_info``."""
+        job = Job(left, right, threshold, flat=flat, rows=rows, l_cat=l_cat, r_cat=r_cat,
+                  cat_mode=cat_mode)
+        out = self.run_jobs([job], capacity=capacity, to_host=to_host, copy=copy)[0]
+        self.last_info = self.last_infos[0]
+        return out
 
-        One kernel launch covers the whole row block; kept records are compacted into a device
-        arena.  If the arena was too small the kernel still counts exactly, so the arena is grown
-        to the exact need and the launch repeated once.  Results larger than
-        ``max_pairs_per_block`` records are produced in several row blocks.
-        ``to_host=False`` leaves the records on the device (kernel-only timing) and returns an
-        empty array; ``copy=False`` returns a view of the engine's pinned arena (valid until the
-        next call).  Counters are in ``self.last_info``."""
-        if left.kind != right.kind:
-            raise TypeError("left and right must be packed for the same score function")
-        fn = self.lib.nsm_jaccard_allpairs if left.kind == "sets" else self.lib.nsm_qratio_allpairs
-        begin, end = rows if rows is not None else (0, left.n_items)
-        n_right = right.n_items
-        info = {"count": 0, "flags": 0, "reruns": 0, "blocks": 0, "d2h_bytes": 0,
-                "stats": dict.fromkeys(nsmlib.STAT_NAMES, 0),
-                "item_pairs": max(0, end - begin) * n_right}
-        self.last_info = info
-        if end <= begin or n_right == 0:
-            return np.zeros(0, dtype=PAIR_DTYPE)
+    def run_jobs(self, jobs: List["Job"], *, capacity: Optional[int] = None, to_host: bool = True,
+                 copy: bool = True) -> List[np.ndarray]:
+        """Runs several all-pairs jobs back to back.
+
+        One kernel launch covers a whole job; kept records are compacted into one of two device
+        arenas, so the device->host copy of job k (on a second stream, into the engine's pinned
+        arena) overlaps the kernel of job k+1.  If an arena was too small the kernel still counts
+        exactly: the arena is grown to the exact need and the launch repeated once.  A job that
+        keeps more than ``max_pairs_per_block`` records is split into left row blocks.
+        ``to_host=False`` leaves the records on the device (kernel-only timing) and returns empty
+        arrays; ``copy=False`` returns views of the pinned arena (valid until the next call)."""
         stream = torch.cuda.current_stream(self.device)
-        ctl = self._arena("ctl", 64, pinned=False)
-        ctl_pin = self._arena("ctl_pin", 64, pinned=True)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        copy_stream = self._copy_stream
+        ctl = [self._arena(f"ctl{i}", 64, pinned=False) for i in range(2)]
+        ctl_pin = [self._arena(f"ctl_pin{i}", 64, pinned=True) for i in range(2)]
+        slot_free: List[Optional[torch.cuda.Event]] = [None, None]   # D2H out of the arena done
 
-        def run(rb: int, re_: int, cap: int):
-            dev = self._arena("out", cap * 16, pinned=False)
+        # expand jobs into row-block work items: (job index, begin, end)
+        work: List[Tuple[int, int, int]] = []
+        infos = []
+        for j, job in enumerate(jobs):
+            if job.left.kind != job.right.kind:
+                raise TypeError("left and right must be packed for the same score function")
+            begin, end = job.rows if job.rows is not None else (0, job.left.n_items)
+            infos.append({"count": 0, "flags": 0, "reruns": 0, "blocks": 0, "d2h_bytes": 0,
+                          "stats": dict.fromkeys(nsmlib.STAT_NAMES, 0),
+                          "item_pairs": max(0, end - begin) * job.right.n_items, "parts": []})
+            if end > begin and job.right.n_items:
+                work.append((j, begin, end))
+        self.last_infos = infos
+
+        def launch(slot: int, item: Tuple[int, int, int], cap: int):
+            j, rb, re_ = item
+            job = jobs[j]
+            fn = self.lib.nsm_jaccard_allpairs if job.left.kind == "sets" else self.lib.nsm_qratio_allpairs
+            if slot_free[slot] is not None:
+                stream.wait_event(slot_free[slot])
+            dev = self._arena(f"out{slot}", cap * 16, pinned=False)
             cap = dev.numel() // 16
-            job = nsmlib.NsmJob(rb, re_, int(flat), int(cat_mode), float(threshold),
-                                l_cat.data_ptr() if l_cat is not None else None,
-                                r_cat.data_ptr() if r_cat is not None else None,
-                                dev.data_ptr(), cap, ctl.data_ptr(), ctl.data_ptr() + 8,
-                                ctl.data_ptr() + 16)
+            c = ctl[slot]
+            cjob = nsmlib.NsmJob(rb, re_, int(job.flat), int(job.cat_mode), float(job.threshold),
+                                 job.l_cat.data_ptr() if job.l_cat is not None else None,
+                                 job.r_cat.data_ptr() if job.r_cat is not None else None,
+                                 dev.data_ptr(), cap, c.data_ptr(), c.data_ptr() + 8, c.data_ptr() + 16)
             if self.time_kernels:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream)
-            nsmlib.check(fn(C.byref(left.struct), C.byref(right.struct), C.byref(job),
+            nsmlib.check(fn(C.byref(job.left.struct), C.byref(job.right.struct), C.byref(cjob),
                             C.c_void_p(stream.cuda_stream)))
             if self.time_kernels:
                 e1.record(stream)
+                self._timed.append((e0, e1))
             self.launches += 1
-            ctl_pin.copy_(ctl, non_blocking=True)
-            stream.synchronize()
-            if self.time_kernels:
-                self.kernel_ms += e0.elapsed_time(e1)
-                self.kernel_launches_timed += 1
-            words = ctl_pin.numpy().view(np.uint64)
-            return int(words[0]), int(words[1]) & 0xffffffff, [int(x) for x in words[2:2 + nsmlib.N_STATS]]
+            ctl_pin[slot].copy_(c, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(stream)
+            return done
 
-        blocks = [(begin, end)]
-        parts: List[Tuple[int, int]] = []   # (offset, count) inside the pinned arena
+        def default_capacity(item) -> int:
+            j, rb, re_ = item
+            have = max((self._buffers[k].numel() // 16 for k in ("out0", "out1") if k in self._buffers),
+                       default=0)
+            want = min(self.max_pairs_per_block, 1 << 24, max(1 << 16, (re_ - rb) * jobs[j].right.n_items // 8))
+            return max(have, want)
+
         host_fill = 0
-        if capacity is None:
-            have = self._buffers["out"].numel() // 16 if "out" in self._buffers else 0
-            capacity = max(have, min(self.max_pairs_per_block, 1 << 24,
-                                     max(1 << 16, info["item_pairs"] // 8)))
-        while blocks:
-            rb, re_ = blocks.pop(0)
-            count, flags, stats = run(rb, re_, capacity)
+        pending = None      # (slot, item, event, capacity)
+        queue = list(work)
+        slot = 0
+        cap_hint = capacity
+        while queue or pending:
+            nxt = None
+            if pending is None and queue:
+                item = queue.pop(0)
+                cap = cap_hint if cap_hint is not None else default_capacity(item)
+                pending = (slot, item, launch(slot, item, cap), cap)
+                slot ^= 1
+            p_slot, p_item, p_done, p_cap = pending
+            p_done.synchronize()
+            words = ctl_pin[p_slot].numpy().view(np.uint64)
+            count, flags = int(words[0]), int(words[1]) & 0xffffffff
+            stats = [int(x) for x in words[2:2 + nsmlib.N_STATS]]
+            j, rb, re_ = p_item
+            info = infos[j]
             if flags & nsmlib.FLAG_OVERFLOW:
                 info["reruns"] += 1
                 if count > self.max_pairs_per_block and re_ - rb > 1:
                     # split by the observed density so that every part should fit
                     n_parts = min(re_ - rb, -(-count // max(1, self.max_pairs_per_block // 2)))
                     cuts = np.linspace(rb, re_, n_parts + 1).astype(np.int64)
-                    blocks[:0] = [(int(a), int(b)) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
-                    capacity = self.max_pairs_per_block
+                    queue[:0] = [(j, int(a), int(b)) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+                    cap_hint = self.max_pairs_per_block
                 else:
-                    capacity = int(count * 1.02) + 1024
-                    blocks.insert(0, (rb, re_))
+                    queue.insert(0, p_item)
+                    cap_hint = int(count * 1.02) + 1024
+                pending = None
+                slot = p_slot
                 continue
+            # launch the next job before copying this one out, so that the two overlap
+            if queue:
+                item = queue.pop(0)
+                cap = cap_hint if cap_hint is not None else default_capacity(item)
+                nxt = (slot, item, launch(slot, item, cap), cap)
+                slot ^= 1
             info["count"] += count
             info["flags"] |= flags
             info["blocks"] += 1
@@ -207,20 +266,45 @@ class Engine:
                 n_bytes = count * 16
                 pin = self._buffers.get("pin")
                 if pin is None or pin.numel() < host_fill + n_bytes:
+                    copy_stream.synchronize()
                     grown = torch.empty(max(host_fill + n_bytes, 2 * (pin.numel() if pin is not None else 0)),
                                         dtype=torch.uint8).pin_memory()
                     if host_fill:
                         grown[:host_fill].copy_(pin[:host_fill])
                     self._buffers["pin"] = pin = grown
-                pin[host_fill:host_fill + n_bytes].copy_(self._buffers["out"][:n_bytes],
-                                                         non_blocking=True)
-                stream.synchronize()
-                host_fill += n_bytes
+                copy_stream.wait_event(p_done)
+                with torch.cuda.stream(copy_stream):
+                    pin[host_fill:host_fill + n_bytes].copy_(self._buffers[f"out{p_slot}"][:n_bytes],
+                                                             non_blocking=True)
+                    freed = torch.cuda.Event()
+                    freed.record(copy_stream)
+                slot_free[p_slot] = freed
+                info["parts"].append((host_fill, n_bytes))
                 info["d2h_bytes"] += n_bytes
-        if not to_host or host_fill == 0:
-            return np.zeros(0, dtype=PAIR_DTYPE)
-        out = self._buffers["pin"][:host_fill].numpy().view(PAIR_DTYPE)
-        return out.copy() if copy else out
+                host_fill += n_bytes
+            pending = nxt
+        copy_stream.synchronize()
+        for ev in slot_free:
+            if ev is not None:
+                stream.wait_event(ev)
+        if self.time_kernels:
+            for e0, e1 in self._timed:
+                self.kernel_ms += e0.elapsed_time(e1)
+                self.kernel_launches_timed += 1
+            self._timed.clear()
+
+        outs = []
+        for info in infos:
+            parts = info.pop("parts")
+            if not to_host or not parts:
+                outs.append(np.zeros(0, dtype=PAIR_DTYPE))
+                continue
+            pin = self._buffers["pin"]
+            # the parts of one job are adjacent in the pinned arena
+            lo, hi = parts[0][0], parts[-1][0] + parts[-1][1]
+            view = pin[lo:hi].numpy().view(PAIR_DTYPE)
+            outs.append(view.copy() if copy else view)
+        return outs
 
     # ------------------------------------------------------------------ roofline denominators
     def microbench(self, kind: int, iters: int = 4096, blocks_per_sm: int = 8,

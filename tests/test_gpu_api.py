@@ -1,0 +1,62 @@
+"""GPU suite: the drop-in Python API (gen_comparable / compare / score functions / Matcher) on the
+CUDA engine against the reference-generated golden vectors."""
+import json
+
+import numpy as np
+import pytest
+
+import golden_cases
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+SCALARS = json.loads((GOLDEN / "scalar_cases.json").read_text(encoding="utf-8"))
+
+
+@pytest.mark.parametrize("name", golden_cases.FRAME_CASES)
+def test_gen_comparable_matches_reference_run(cuda_engine, name):
+    golden_cases.check_case(name)
+
+
+def _check_scalar(fn, case):
+    want = case["result"]
+    if want.startswith("raises:"):
+        with pytest.raises(Exception) as ei:
+            fn(case["left"], case["right"])
+        assert type(ei.value).__name__ == want.split(":")[1]
+    else:
+        assert float(fn(case["left"], case["right"])).hex() == want
+
+
+def test_scalar_score_functions_run_on_the_gpu(cuda_engine):
+    from napkon_string_matching.compare import score_functions as sf
+
+    before = cuda_engine.launches
+    for case in SCALARS["jaccard_hand"]["cases"]:
+        _check_scalar(sf.intersection_vs_union, case)
+    for case in SCALARS["fuzzy_hand"]["cases"]:
+        _check_scalar(sf.fuzzy_match, case)
+    assert cuda_engine.launches - before >= len(SCALARS["jaccard_hand"]["cases"])
+    assert sf.join_sorted(["beta", "Alpha"]) == "Alpha beta"
+
+
+def test_compare_terms_with_gpu_score_functions(cuda_engine):
+    from napkon_string_matching.compare import score_functions as sf
+    from napkon_string_matching.types.comparable_data import ComparableData
+
+    for func, fn in (("jaccard", sf.intersection_vs_union), ("fuzzy", sf.fuzzy_match)):
+        for case in SCALARS[f"compare_terms_{func}"]["cases"]:
+            _check_scalar(lambda l, r: ComparableData.compare_terms(l, r, fn), case)
+
+
+def test_one_against_many_matches_the_scalar_calls(cuda_engine):
+    from napkon_string_matching.compare import score_functions as sf
+
+    synonyms = ["Dialyse", "Renal Dialysis", "Sonstiges", "Hatte Sie Dialyse?", "", "dialyse nach entlassung"]
+    many = sf.fuzzy_match_many("Dialyse nach Entlassung", synonyms)
+    assert [float(x).hex() for x in many] == \
+        [float(sf.fuzzy_match("Dialyse nach Entlassung", s)).hex() for s in synonyms]
+    assert many[-1] == 1.0 and many[4] == 0.0
+    sets = [["a", "b"], ["b"], ["x", "y", "z"], ["a", "b", "c", "d"]]
+    many = sf.intersection_vs_union_many(["a", "b", "c"], sets)
+    assert list(many) == [2 / 3, 1 / 3, 0.0, 3 / 4]
