@@ -335,6 +335,40 @@ def pack_suffix_id_sets(lens: np.ndarray, flat_ids: np.ndarray, n_vocab: int,
     return finish_sets(item_level_off, new_off, codes, n_vocab)
 
 
+def pack_part_id_sets(part_lens: np.ndarray, flat_ids: np.ndarray, n_vocab: int,
+                      rank: np.ndarray | None = None) -> PackedSets:
+    """Integer fast path for list-valued columns whose parts hold several tokens (``Term``):
+    ``part_lens[i, q]`` ids of part q of item i follow one another in ``flat_ids`` (absent parts
+    have length 0); level j is the id set of the last j+1 present parts (Q2)."""
+    part_lens = np.asarray(part_lens, dtype=np.int64)
+    n, n_parts = part_lens.shape
+    flat_ids = np.asarray(flat_ids, dtype=np.int64)
+    if rank is not None:
+        flat_ids = np.asarray(rank)[flat_ids]
+    present = part_lens > 0
+    k = present.sum(axis=1)
+    item_level_off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(k, out=item_level_off[1:])
+    item_len = part_lens.sum(axis=1)
+    item_end = np.cumsum(item_len)
+    # suffix sizes: ids in parts q..last, for every present part q, deepest suffix last
+    suffix = np.cumsum(part_lens[:, ::-1], axis=1)[:, ::-1]          # ids from part q to the end
+    # levels of item i, j = 0..k-1: the present parts taken from the back
+    order = np.argsort(~present[:, ::-1], axis=1, kind="stable")     # present parts from the back, first
+    back_idx = n_parts - 1 - order                                   # part index of the j-th present part from the back
+    level_sizes_raw = np.take_along_axis(suffix, back_idx, axis=1)   # [n, n_parts]; valid for j < k
+    valid = np.arange(n_parts)[None, :] < k[:, None]
+    raw_sizes = level_sizes_raw[valid]
+    level_item = np.repeat(np.arange(n, dtype=np.int64), k)
+    raw_off = np.zeros(len(raw_sizes) + 1, dtype=np.int64)
+    np.cumsum(raw_sizes, out=raw_off[1:])
+    within = np.arange(int(raw_off[-1]), dtype=np.int64) - np.repeat(raw_off[:-1], raw_sizes)
+    src = np.repeat(item_end[level_item] - raw_sizes, raw_sizes) + within
+    codes = flat_ids[src]
+    new_off, codes = _sort_unique_levels(raw_off, codes)
+    return finish_sets(item_level_off, new_off, codes, n_vocab)
+
+
 # ------------------------------------------------------------------------------------------
 # strings
 # ------------------------------------------------------------------------------------------

@@ -172,3 +172,49 @@ def cohort_frames(n_items: int, names=("hap", "pop", "suep")) -> Dict[str, pd.Da
     seeds = {"hap": SEED_LEFT, "pop": SEED_RIGHT, "suep": SEED_THIRD}
     vocab = vocabulary()
     return {n: questionnaire_frame(n_items, seeds[n], vocab, n) for n in names}
+
+
+def term_level_sets(n_items: int, seed: int, n_vocab: int = 20000):
+    """cfg1 / cfg5 item shape (``Term = [*header, question, parameter]``) drawn directly as
+    integer word ids, without Python strings, for the 200k..1M item benchmark shapes: per item up
+    to four parts (header absent 40 % / one 30 % / two 30 %, two words each from the 400 most
+    frequent words; question 3-9 words; parameter 1-5 words), Zipf(1.0) over ``n_vocab`` words.
+    Returns ``(part_lens[n_items, 4], flat_ids)``: the word counts of (header1, header2, question,
+    parameter) — 0 for an absent header — and all word ids, item by item, part by part.
+    Level j of an item is the id set of its last j+1 present parts (Q2)."""
+    rng = np.random.default_rng(seed)
+    u = rng.random(n_items)
+    n_head = np.where(u < 0.4, 0, np.where(u < 0.7, 1, 2))
+    part_lens = np.zeros((n_items, 4), dtype=np.int64)
+    part_lens[:, 0] = np.where(n_head == 2, 2, 0)
+    part_lens[:, 1] = np.where(n_head >= 1, 2, 0)
+    part_lens[:, 2] = rng.integers(3, 10, size=n_items)
+    part_lens[:, 3] = rng.integers(1, 6, size=n_items)
+    total = int(part_lens.sum())
+    body_cdf = np.cumsum(zipf_probs(n_vocab)); body_cdf[-1] = 1.0
+    head_cdf = np.cumsum(zipf_probs(400)); head_cdf[-1] = 1.0
+    is_head = np.repeat(np.tile(np.array([True, True, False, False]), n_items), part_lens.reshape(-1))
+    r = rng.random(total)
+    flat = np.where(is_head, np.searchsorted(head_cdf, r, side="right"),
+                    np.searchsorted(body_cdf, r, side="right")).astype(np.uint32)
+    return part_lens, flat
+
+
+def definition_level_sets(n_items: int, seed: int = SEED_DEFS, n_vocab: int = 20000):
+    """cfg4 right-hand side at scale (GECCO-style ``Term = [category, parameter, choice]``) as
+    integer word ids; same return convention as :func:`term_level_sets` with three parts:
+    category 1-2 words from the 200 most frequent, parameter 1-5 words, choice absent 40 % or
+    1-3 words."""
+    rng = np.random.default_rng(seed)
+    part_lens = np.zeros((n_items, 3), dtype=np.int64)
+    part_lens[:, 0] = rng.integers(1, 3, size=n_items)
+    part_lens[:, 1] = rng.integers(1, 6, size=n_items)
+    part_lens[:, 2] = np.where(rng.random(n_items) < 0.6, rng.integers(1, 4, size=n_items), 0)
+    total = int(part_lens.sum())
+    body_cdf = np.cumsum(zipf_probs(n_vocab)); body_cdf[-1] = 1.0
+    cat_cdf = np.cumsum(zipf_probs(200)); cat_cdf[-1] = 1.0
+    is_cat = np.repeat(np.tile(np.array([True, False, False]), n_items), part_lens.reshape(-1))
+    r = rng.random(total)
+    flat = np.where(is_cat, np.searchsorted(cat_cdf, r, side="right"),
+                    np.searchsorted(body_cdf, r, side="right")).astype(np.uint32)
+    return part_lens, flat

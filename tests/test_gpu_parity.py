@@ -197,3 +197,53 @@ def test_fuzzy_empty_items_and_flags(engine):
     assert info["flags"] & nsmlib.FLAG_EMPTY_ITEM
     got = {(int(a), int(b)): s for a, b, s in zip(out["left"], out["right"], out["score"])}
     assert got == {(0, 1): 0.0, (1, 0): 0.5}
+
+
+def test_jaccard_full_size_properties(engine):
+    """BASELINE configs[1] scale (50k-item cohorts): too big for the oracle to enumerate, so
+    check properties that do not depend on size: row blocks partition the result, the kept set
+    is symmetric under swapping the sides, kept scores equal the oracle's on a sample, and a
+    sample of pairs that were not kept score below the threshold in the oracle."""
+    thr = 0.1
+    lens, flat = syn.token_id_level_sets(50_000, syn.SEED_LEFT)
+    pl = pack.pack_suffix_id_sets(lens, flat, 30000)
+    lens, flat = syn.token_id_level_sets(50_000, syn.SEED_RIGHT)
+    pr = pack.pack_suffix_id_sets(lens, flat, 30000)
+    dl, dr = engine.upload(pl), engine.upload(pr)
+    rows = (10_000, 30_000)
+    whole = engine.all_pairs(dl, dr, thr, rows=rows)
+    n_whole = len(whole)
+    assert n_whole == engine.last_info["count"] > 10_000_000
+    assert whole["left"].min() >= rows[0] and whole["left"].max() < rows[1]
+    key = whole["left"].astype(np.uint64) * np.uint64(pr.n_items) + whole["right"]
+    order = np.argsort(key, kind="stable")
+    key, score = key[order], whole["score"][order]
+    assert np.all(key[1:] != key[:-1]), "a pair was emitted twice"
+    # (1) row blocks partition the result
+    parts = 0
+    for b, e in ((10_000, 10_001), (10_001, 17_333), (17_333, 30_000)):
+        engine.all_pairs(dl, dr, thr, rows=(b, e), to_host=False)
+        parts += engine.last_info["count"]
+    assert parts == n_whole
+    # (2) symmetry: right x left keeps the transposed set with the same scores
+    swapped = engine.all_pairs(dr, dl, thr)
+    sel = (swapped["right"] >= rows[0]) & (swapped["right"] < rows[1])
+    skey = swapped["right"][sel].astype(np.uint64) * np.uint64(pr.n_items) + swapped["left"][sel]
+    sorder = np.argsort(skey, kind="stable")
+    assert np.array_equal(skey[sorder], key)
+    assert np.array_equal(swapped["score"][sel][sorder].view(np.uint64), score.view(np.uint64))
+    del swapped
+    # (3) kept scores are the oracle's, bit for bit, on a sample
+    rng = np.random.default_rng(1)
+    pick = rng.choice(n_whole, size=50_000, replace=False)
+    want, _ = c_oracle.score_pairs(pl, pr, whole["left"][pick], whole["right"][pick])
+    assert np.array_equal(want.view(np.uint64), whole["score"][pick].view(np.uint64))
+    assert np.all(whole["score"] >= thr)
+    # (4) pairs that were not kept are below the threshold
+    li = rng.integers(rows[0], rows[1], size=300_000).astype(np.uint32)
+    ri = rng.integers(0, pr.n_items, size=300_000).astype(np.uint32)
+    probe = li.astype(np.uint64) * np.uint64(pr.n_items) + ri
+    pos = np.searchsorted(key, probe)
+    kept = (pos < len(key)) & (key[np.minimum(pos, len(key) - 1)] == probe)
+    got, _ = c_oracle.score_pairs(pl, pr, li, ri)
+    assert np.array_equal(got >= thr, kept)
