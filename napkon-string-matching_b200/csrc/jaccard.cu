@@ -22,7 +22,8 @@
 //   B  BOUND   (per step, integer + fp32 round-up, branch-free) exact head intersection by
 //              popcount plus an upper bound of the tail intersection from the signatures bounds
 //              every level score; compare_terms' weights are accumulated with directed rounding.
-//              Six steps, straight-line; the weight of any later steps is granted in full.
+//              Six steps, straight-line, in two halves (steps 1..D, then the rest for the pairs
+//              whose bound can still reach the threshold); later steps' weight is granted in full.
 //   C  EXACT   per used level the exact |A & B| (popcount; only if both tail signatures collide,
 //              a warp-cooperative intersection of the tail ids), the reference's int/int float64
 //              division and its accumulation order; score >= threshold in float64.
@@ -36,9 +37,9 @@ constexpr int JT_THREADS = 128;   // right items per block (= threads per CTA)
 constexpr int JT_CTAS = 5;        // resident CTAs per SM the kernel is sized for
 constexpr int J_UNIT_LEFT = 512;  // left items per unit
 constexpr int J_SLOTS = 10;       // steps staged per item (pack.py SLOT_CAP)
-constexpr int J_RCP = 512;        // reciprocal table size
+constexpr int J_RCP = 256;        // reciprocal table size
 constexpr int J_WARPS = JT_THREADS / 32;
-constexpr int J_OUT = 64;         // staged output records per warp
+constexpr int J_OUT = 48;         // staged output records per warp
 constexpr int J_UNROLL = 6;       // steps of stage B, all straight-line code
 constexpr int J_AUNROLL = 4;      // left items per round of stage A
 constexpr int J_QA = 32 + 32 * J_AUNROLL;  // queue A capacity
@@ -48,6 +49,7 @@ struct JaccardParams {
     nsm_job_t job;
     float thr_lo;        // filter threshold (see filter_threshold); -inf: everything passes
     uint32_t any_depth;  // D of stage A; 0: use the packed all-level item_any
+    uint32_t bound_split;  // stage B tests the bound after this many steps (1..J_UNROLL)
     uint32_t n_lchunks, n_rblocks;
 };
 
@@ -59,6 +61,8 @@ struct __align__(16) JaccardSmem {
     uint32_t r_k[JT_THREADS];
     float rcp_up[J_RCP];
     uint32_t qa[J_WARPS][J_QA];
+    uint32_t qm[J_WARPS][64];   // survivors of the first D bound steps ...
+    float qm_ub[J_WARPS][64];   // ... and their partial bound
     uint32_t qb[J_WARPS][64];
     uint16_t l_k[J_UNIT_LEFT];
     unsigned long long stats[NSM_N_STATS];
@@ -122,7 +126,7 @@ __device__ __forceinline__ uint32_t bound_intersection(const ulonglong2 &A, uint
     return min(__popcll(A.x & B.x) + it, min(ia & 0xffffu, ib & 0xffffu));
 }
 
-template <bool DEEP>
+template <bool DEEP, int SPLIT>
 __global__ void __launch_bounds__(JT_THREADS, JT_CTAS)
 jaccard_allpairs_kernel(const JaccardParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -244,7 +248,7 @@ jaccard_allpairs_kernel(const JaccardParams p) {
         // The funnel as one loop, so that each stage's code exists once: fill queue A from stage
         // A until it holds a warp's worth (or the unit is exhausted), run stage B on 32 entries,
         // run stage C whenever queue B holds 32 (or everything before it is done).
-        uint32_t qa_n = 0, qb_n = 0, li_next = 0;  // warp-uniform
+        uint32_t qa_n = 0, qm_n = 0, qb_n = 0, li_next = 0;  // warp-uniform
         while (true) {
             // ---- stage A: left items x my right item ----------------------------------------
             while (qa_n < 32 && li_next < nl) {
@@ -270,10 +274,25 @@ jaccard_allpairs_kernel(const JaccardParams p) {
                 li_next += J_AUNROLL;
             }
             const bool unit_done = li_next >= nl;
-            if (qa_n == 0 && qb_n == 0 && unit_done) break;
+            if (qa_n == 0 && qm_n == 0 && qb_n == 0 && unit_done) break;
             __syncwarp();
 
             // ---- stage B: fp32 upper bound of one surviving pair per lane -----------------
+            // Two halves with a queue in between: steps 1..D first (D as in stage A: once they
+            // are known, bound + remaining weight can already fall short of the threshold), then
+            // steps D+1..J_UNROLL for the pairs that are still alive.
+            auto bound_step = [&](uint32_t t, uint32_t li, uint32_t rc, uint32_t kmax, float ub) {
+                // steps beyond kmax read a repeated level and get weight 0
+                const uint32_t sr = min(t, SR) - 1;
+                const size_t at = (size_t)(min(t, SL) - 1) * p.L.n_items + l0 + li;
+                const uint32_t ia = __ldg(p.L.slot_info + at), ib = s.r_info[sr][rc];
+                const uint32_t ih = bound_intersection(__ldg(l_slot_ht + at), ia, s.r_ht[sr][rc], ib,
+                                                       exact_bits);
+                const uint32_t uh = min((ia & 0xffffu) + (ib & 0xffffu) - ih,
+                                        (uint32_t)J_RCP - 1);  // 1/255 >= 1/u beyond
+                const float w = t <= kmax ? (flat ? 1.0f : pow2_neg(t)) : 0.0f;
+                return __fmaf_ru(__fmul_ru((float)ih, s.rcp_up[uh]), w, ub);
+            };
             if (qa_n >= 32 || (unit_done && qa_n)) {
                 const uint32_t take = min(qa_n, 32u);
                 qa_n -= take;
@@ -282,23 +301,41 @@ jaccard_allpairs_kernel(const JaccardParams p) {
                 const uint32_t li = entry >> 5, rc = (warp << 5) | (entry & 31u);
                 const uint32_t kl = s.l_k[li], c_kr = s.r_k[rc];
                 bool pass = active;
+                float ub = 0.0f;
                 if (active && !pass_all && kl != 0 && c_kr != 0) {
                     const uint32_t kmax = flat ? 1u : max(kl, c_kr);
-                    float ub = 0.0f;
                     ++st_bound;
 #pragma unroll
-                    for (uint32_t t = 1; t <= (uint32_t)J_UNROLL; ++t) {
-                        // steps beyond kmax read a repeated level and get weight 0
-                        const uint32_t sr = min(t, SR) - 1;
-                        const size_t at = (size_t)(min(t, SL) - 1) * p.L.n_items + l0 + li;
-                        const uint32_t ia = __ldg(p.L.slot_info + at), ib = s.r_info[sr][rc];
-                        const uint32_t ih = bound_intersection(__ldg(l_slot_ht + at), ia, s.r_ht[sr][rc],
-                                                               ib, exact_bits);
-                        const uint32_t uh = min((ia & 0xffffu) + (ib & 0xffffu) - ih,
-                                                (uint32_t)J_RCP - 1);  // 1/511 >= 1/u beyond
-                        const float w = t <= kmax ? (flat ? 1.0f : pow2_neg(t)) : 0.0f;
-                        ub = __fmaf_ru(__fmul_ru((float)ih, s.rcp_up[uh]), w, ub);
-                    }
+                    for (uint32_t t = 1; t <= (uint32_t)J_UNROLL; ++t)
+                        if (t <= (uint32_t)SPLIT) ub = bound_step(t, li, rc, kmax, ub);
+                    // weights still to come after step D: 2^-D - 2^-kmax
+                    const float rem = kmax > (uint32_t)SPLIT
+                        ? __fsub_ru(pow2_neg(SPLIT), pow2_neg(kmax)) : 0.0f;
+                    pass = __fadd_ru(ub, rem) >= p.thr_lo;
+                }
+                const unsigned m = __ballot_sync(FULL_MASK, pass);
+                if (pass) {
+                    const uint32_t at = qm_n + __popc(m & lanemask_lt());
+                    s.qm[warp][at] = entry;
+                    s.qm_ub[warp][at] = ub;
+                }
+                qm_n += __popc(m);
+                __syncwarp();
+            }
+            if (qm_n >= 32 || (unit_done && qa_n == 0 && qm_n)) {
+                const uint32_t take = min(qm_n, 32u);
+                qm_n -= take;
+                const bool active = lane < take;
+                const uint32_t entry = active ? s.qm[warp][qm_n + lane] : 0u;
+                float ub = active ? s.qm_ub[warp][qm_n + lane] : 0.0f;
+                const uint32_t li = entry >> 5, rc = (warp << 5) | (entry & 31u);
+                const uint32_t kl = s.l_k[li], c_kr = s.r_k[rc];
+                bool pass = active;
+                if (active && !pass_all && kl != 0 && c_kr != 0) {
+                    const uint32_t kmax = flat ? 1u : max(kl, c_kr);
+#pragma unroll
+                    for (uint32_t t = 2; t <= (uint32_t)J_UNROLL; ++t)
+                        if (t > (uint32_t)SPLIT) ub = bound_step(t, li, rc, kmax, ub);
                     // steps beyond the unrolled ones are not bounded individually: all their
                     // weight, 2^-UNROLL - 2^-kmax, is granted (pairs this lets through are within
                     // 2^-UNROLL of the threshold and get their exact score in stage C)
@@ -315,7 +352,7 @@ jaccard_allpairs_kernel(const JaccardParams p) {
             // ---- stage C: exact score of one candidate per lane ---------------------------
             // The step loop is warp-uniform (lanes whose pair has fewer steps idle) so that the
             // rare tail intersections can be computed by the whole warp.
-            if (qb_n >= 32 || (unit_done && qa_n == 0 && qb_n)) {
+            if (qb_n >= 32 || (unit_done && qa_n == 0 && qm_n == 0 && qb_n)) {
                 const uint32_t take = min(qb_n, 32u);
                 qb_n -= take;
                 const bool active = lane < take;
@@ -430,16 +467,25 @@ jaccard_allpairs_kernel(const JaccardParams p) {
     }
 }
 
-template <bool DEEP>
+template <bool DEEP, int SPLIT>
 static int launch_jaccard(const JaccardParams &p, uint64_t n_units, cudaStream_t stream) {
     const size_t smem = sizeof(JaccardSmem);
-    NSM_CUDA_CHECK(cudaFuncSetAttribute(jaccard_allpairs_kernel<DEEP>,
+    NSM_CUDA_CHECK(cudaFuncSetAttribute(jaccard_allpairs_kernel<DEEP, SPLIT>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint64_t resident = (uint64_t)JT_CTAS * (uint64_t)sm_count();
     const uint32_t grid = (uint32_t)(n_units < resident ? n_units : resident);
-    jaccard_allpairs_kernel<DEEP><<<grid, JT_THREADS, smem, stream>>>(p);
+    jaccard_allpairs_kernel<DEEP, SPLIT><<<grid, JT_THREADS, smem, stream>>>(p);
     NSM_CUDA_CHECK(cudaGetLastError());
     return NSM_OK;
+}
+
+template <bool DEEP>
+static int launch_jaccard_split(const JaccardParams &p, uint64_t n_units, cudaStream_t stream) {
+    switch (p.bound_split) {
+        case 1: return launch_jaccard<DEEP, 1>(p, n_units, stream);
+        case 2: return launch_jaccard<DEEP, 2>(p, n_units, stream);
+        default: return launch_jaccard<DEEP, J_UNROLL>(p, n_units, stream);
+    }
 }
 
 }  // namespace nsm
@@ -471,14 +517,21 @@ extern "C" int nsm_jaccard_allpairs(const nsm_sets_t *left, const nsm_sets_t *ri
     // an item whose levels do not all fit its side's slots needs the CSR arrays for deep steps
     const bool l_deep = left->max_levels > left->n_slots + 1;
     const bool r_deep = right->max_levels > right->n_slots + 1;
-    // stage A depth: the smallest D with 2^-D < threshold, if both sides hold D steps in their
-    // slots (or all their levels); otherwise the packed all-level union is used
+    // Depth D: the smallest D such that steps beyond D cannot lift a zero score to the threshold,
+    // 2^-D - 2^-Kmax < threshold with Kmax the deepest schedule of any pair.  Stage A uses it if
+    // both sides hold D steps in their slots (or all their levels), otherwise the packed all-level
+    // union; stage B tests its bound for the first time after D steps.
     p.any_depth = 0;
+    p.bound_split = J_UNROLL;
     if (p.thr_lo > 0.0f && !job->flat) {
+        const uint32_t kmax = left->max_levels > right->max_levels ? left->max_levels : right->max_levels;
+        const float w_last = kmax < 120 ? ldexpf(1.0f, -(int)kmax) : 0.0f;
         uint32_t d = 1;
-        while (d < 64 && ldexpf(1.0f, -(int)d) >= p.thr_lo) ++d;
+        while (d < 64 && !(ldexpf(1.0f, -(int)d) - w_last < p.thr_lo)) ++d;  // exact: powers of two
         if ((d <= left->n_slots || !l_deep) && (d <= right->n_slots || !r_deep))
             p.any_depth = d < (uint32_t)J_SLOTS ? d : (uint32_t)J_SLOTS;
+        // splitting pays when few pairs survive the first half, i.e. at high thresholds (small D)
+        p.bound_split = d <= 2 ? d : (uint32_t)J_UNROLL;
     }
     const uint32_t n_rows = job->l_row_end - job->l_row_begin;
     p.n_lchunks = (n_rows + J_UNIT_LEFT - 1) / J_UNIT_LEFT;
@@ -488,6 +541,6 @@ extern "C" int nsm_jaccard_allpairs(const nsm_sets_t *left, const nsm_sets_t *ri
         set_error("too many work units (%llu); split the left row block", (unsigned long long)n_units);
         return NSM_ERR_UNSUPPORTED;
     }
-    return (l_deep || r_deep) ? launch_jaccard<true>(p, n_units, stream)
-                              : launch_jaccard<false>(p, n_units, stream);
+    return (l_deep || r_deep) ? launch_jaccard_split<true>(p, n_units, stream)
+                              : launch_jaccard_split<false>(p, n_units, stream);
 }
