@@ -82,13 +82,19 @@ typedef struct nsm_sets {
  * (join_sorted + default_process, score_functions.py:16-27), one alphabet code per code point. */
 typedef struct nsm_strings {
     const uint32_t *item_level_off; /* [n_items + 1] */
-    const uint32_t *level_chr_off;  /* [n_levels + 1] */
-    const uint8_t *chr;             /* [level_chr_off[n_levels]] codes < n_alphabet */
+    const uint32_t *level_chr_off;  /* [n_levels] start of the level's string in chr, multiple of 8 */
+    const uint32_t *level_len;      /* [n_levels] length in code points */
+    const uint8_t *chr;             /* codes < n_alphabet; every string padded to 8 bytes */
     uint32_t n_items;
     uint32_t n_levels;
     uint32_t max_levels;
     uint32_t max_len;    /* longest level string on this side */
     uint32_t n_alphabet; /* shared by both sides, <= 255 */
+    uint32_t reserved_;
+    /* Items are ordered by the 64-bit words their longest level string needs: items
+     * [class_end[w-1], class_end[w]) need w+1 words (class_end[7] == n_items; longer strings are
+     * not supported).  The kernel runs every class of the right side with its own width. */
+    uint32_t class_end[8];
 } nsm_strings_t;
 
 /* What to compare and where the kept pairs go. */
@@ -116,6 +122,9 @@ typedef struct nsm_job {
 
 int nsm_version(void);
 const char *nsm_last_error(void);
+/* Number of kernels the last nsm_*_allpairs / nsm_microbench call of this thread launched
+ * (the fuzzy path launches one kernel per word-count class of the right side). */
+int nsm_last_launch_count(void);
 
 /* Replaces the pair loop of gen_comparable (comparable_data.py:223-243) for
  * score_func == "intersection_vs_union" (score_functions.py:6-13). */

@@ -8,6 +8,11 @@
 namespace nsm {
 
 static thread_local char g_error[512] = "";
+static thread_local int g_launches = 0;
+
+void reset_launch_count() { g_launches = 0; }
+void count_launch() { ++g_launches; }
+int launch_count() { return g_launches; }
 
 void set_error(const char *fmt, ...) {
     va_list ap;
@@ -40,6 +45,7 @@ float filter_threshold(double threshold) {
 }
 
 int prepare_job(const nsm_job_t *job, uint32_t n_left, cudaStream_t stream) {
+    reset_launch_count();
     if (job->l_row_begin > job->l_row_end || job->l_row_end > n_left) {
         set_error("row block [%u, %u) outside the %u left items", job->l_row_begin, job->l_row_end,
                   n_left);
@@ -69,3 +75,5 @@ int prepare_job(const nsm_job_t *job, uint32_t n_left, cudaStream_t stream) {
 extern "C" int nsm_version(void) { return NSM_VERSION; }
 
 extern "C" const char *nsm_last_error(void) { return nsm::g_error; }
+
+extern "C" int nsm_last_launch_count(void) { return nsm::g_launches; }

@@ -475,6 +475,7 @@ static int launch_jaccard(const JaccardParams &p, uint64_t n_units, cudaStream_t
     const uint64_t resident = (uint64_t)JT_CTAS * (uint64_t)sm_count();
     const uint32_t grid = (uint32_t)(n_units < resident ? n_units : resident);
     jaccard_allpairs_kernel<DEEP, SPLIT><<<grid, JT_THREADS, smem, stream>>>(p);
+    count_launch();
     NSM_CUDA_CHECK(cudaGetLastError());
     return NSM_OK;
 }

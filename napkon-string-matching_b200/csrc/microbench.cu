@@ -59,6 +59,8 @@ extern "C" int nsm_microbench(int kind, uint32_t blocks, uint32_t threads, uint3
         return NSM_ERR_BAD_ARG;
     }
     uint64_t per_iter = 0;
+    reset_launch_count();
+    count_launch();
     switch (kind) {
         case 0: microbench_kernel<0><<<blocks, threads, 0, stream>>>(iters, sink); per_iter = 4 * MB_CHAINS; break;
         case 1: microbench_kernel<1><<<blocks, threads, 0, stream>>>(iters, sink); per_iter = 4 * MB_CHAINS; break;  // one IADD3 each

@@ -10,6 +10,8 @@
 namespace nsm {
 
 void set_error(const char *fmt, ...);
+void reset_launch_count();
+void count_launch();
 
 #define NSM_CUDA_CHECK(expr)                                                              \
     do {                                                                                  \

@@ -9,94 +9,155 @@
 //
 // One pair per lane: every thread owns one right item and keeps the pattern-match masks M[c] of
 // the right level string it is currently scoring in shared memory, transposed as [c][word][thread]
-// so that the 32 lanes of a warp read 32 consecutive 64-bit words (no bank conflicts).  The left
-// tile's level strings are staged in shared memory and used as the text: all threads of the CTA
-// consume the same character at the same time, so the inner loop has a uniform trip count and no
-// divergence.  Strings longer than 64 characters use W words per thread with the add carry
-// chained through registers (W is a template parameter, <= 8, i.e. 512 characters).
+// so that the 32 lanes of a warp read 32 consecutive 64-bit words (no bank conflicts).  A unit of
+// work is one block of right items x a group of left tiles; the left tile's level strings are
+// staged in shared memory (8-byte aligned, read 8 characters at a time) and used as the text: all
+// threads of the CTA consume the same character at the same time, so the inner loop has a uniform
+// trip count, no divergence, and the mask loads of the next characters do not depend on S.
+// Strings longer than 64 characters use W words per thread with the add carry chained through
+// registers (W is a template parameter, <= 8, i.e. 512 characters).
 //
-// compare_terms' level schedule runs as the outer loop (step t uses level min(t, K-1) on both
-// sides, weight 2^-t), so a thread rebuilds its masks at most K_right times per tile; partial
-// scores of the tile's pairs live in shared memory as float64 and are accumulated in the
-// reference's order.  Pairs with score >= threshold are compacted with one atomic per warp.
+// Two instantiations per W:
+//   LEVELS = false  items have one level (the flat score function, the `Question` column of
+//                   config 3): masks are built once per unit, every pair is scored and emitted
+//                   as soon as its LCS is known.
+//   LEVELS = true   compare_terms' schedule runs as the outer loop per left tile (step t uses
+//                   level min(t, K-1) on both sides, weight 2^-t); a thread rebuilds its masks at
+//                   most K_right times per tile; partial scores of the tile's pairs live in
+//                   shared memory as float64 and are accumulated in the reference's order.
+// Pairs with score >= threshold are compacted with one atomic per warp.
 #include "nsm_common.cuh"
 
 namespace nsm {
 
-constexpr int Q_MAX_THREADS = 256;
-constexpr int Q_TILE_LEFT = 32;       // left items per tile (upper bound)
-constexpr int Q_CHR_CAP = 24 * 1024;  // bytes of left level strings staged per tile
-constexpr int Q_LEV_CAP = 2048;       // left levels staged per tile
+constexpr int Q_MAX_THREADS = 512;
+constexpr int Q_TILE_FLAT = 32;       // left items per tile, one level each
+constexpr int Q_TILE_LEVELS = 8;      // left items per tile when partial scores are kept
+constexpr int Q_GROUP = 16;           // left tiles per unit
+constexpr int Q_CHR_CAP = 16 * 1024;  // bytes of left level strings staged per tile
+constexpr int Q_LEV_CAP = 1024;       // left levels staged per tile
 constexpr int Q_MAX_WORDS = 8;
-constexpr size_t Q_SMEM_BUDGET = 200 * 1024;
+constexpr size_t Q_SMEM_BUDGET = 220 * 1024;
 
 struct QratioParams {
     nsm_strings_t L, R;
     nsm_job_t job;
-    uint32_t tile_left, n_ltiles, n_rtiles;
-    uint32_t threads;   // right items per tile
+    uint32_t tile_left, n_ltiles, n_lgroups, n_rblocks;
+    uint32_t threads;   // right items per block
     uint32_t n_alpha;   // rows of the mask table
+    uint32_t r_begin, r_end;  // the right items of this launch (one word-count class)
 };
 
 struct QratioLayout {  // offsets into dynamic shared memory
-    size_t pm, acc, chr, lev_off, item_g0, cat, misc, total;
+    size_t pm, acc, chr, lev_off, lev_len, item_g0, cat, misc, total;
 };
 
 __host__ __device__ inline QratioLayout qratio_layout(uint32_t n_alpha, uint32_t words,
-                                                      uint32_t threads, uint32_t tile_left) {
+                                                      uint32_t threads, uint32_t tile_left,
+                                                      bool levels) {
     QratioLayout l;
     size_t o = 0;
     l.pm = o;      o += (size_t)n_alpha * words * threads * 8;
-    l.acc = o;     o += (size_t)tile_left * threads * 8;
+    l.acc = o;     o += levels ? (size_t)tile_left * threads * 8 : 0;
     l.chr = o;     o += Q_CHR_CAP;
-    l.lev_off = o; o += (Q_LEV_CAP + 1) * 4;
-    o = (o + 7) & ~(size_t)7;
-    l.cat = o;     o += Q_TILE_LEFT * 8;
-    l.item_g0 = o; o += (Q_TILE_LEFT + 1) * 4;
+    l.cat = o;     o += Q_TILE_FLAT * 8;
+    l.lev_off = o; o += Q_LEV_CAP * 4;
+    l.lev_len = o; o += Q_LEV_CAP * 4;
+    l.item_g0 = o; o += (Q_TILE_FLAT + 1) * 4;
     l.misc = o;    o += 16;
     l.total = (o + 15) & ~(size_t)15;
     return l;
 }
 
+// LCS length of my pattern (masks in shared memory, column `pm`) and a text of n characters that
+// starts 8-byte aligned at `text` in shared memory.  Uniform over the CTA.
 template <int W>
+__device__ __forceinline__ uint32_t lcs_bitparallel(const uint64_t *__restrict__ pm, uint32_t nthr,
+                                                    const uint8_t *__restrict__ text, uint32_t n) {
+    uint64_t S[W];
+#pragma unroll
+    for (int x = 0; x < W; ++x) S[x] = ~0ull;
+    const uint64_t *text8 = reinterpret_cast<const uint64_t *>(text);
+    const size_t row_stride = (size_t)W * nthr;
+    auto step = [&](uint32_t c) {
+        const uint64_t *row = pm + c * row_stride;
+        uint32_t carry = 0;
+#pragma unroll
+        for (int x = 0; x < W; ++x) {
+            const uint64_t M = row[(size_t)x * nthr];
+            const uint64_t u = S[x] & M;
+            const uint64_t sum = S[x] + u;
+            const uint64_t sum2 = sum + carry;
+            if (W > 1) carry = (sum < u) | (sum2 < sum);
+            S[x] = sum2 | (S[x] - u);
+        }
+    };
+    uint32_t j = 0;
+    for (; j + 8 <= n; j += 8) {  // eight characters per shared-memory word
+        const uint64_t w8 = text8[j >> 3];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) step((uint32_t)(w8 >> (8 * q)) & 0xffu);
+    }
+    if (j < n) {
+        const uint64_t w8 = text8[j >> 3];
+        for (uint32_t q = 0; j + q < n; ++q) step((uint32_t)(w8 >> (8 * q)) & 0xffu);
+    }
+    uint32_t lcs = 0;
+#pragma unroll
+    for (int x = 0; x < W; ++x) lcs += __popcll(~S[x]);
+    return lcs;
+}
+
+// QRatio(a, b) / 100 from the counts: 0 when either processed string is empty, else
+// ((1.0 - dist / lensum) * 100) / 100 with dist = lensum - 2 LCS — this exact operation order.
+__device__ __forceinline__ double qratio_from_lcs(uint32_t m, uint32_t n, uint32_t lcs) {
+    if (m == 0 || n == 0) return 0.0;
+    const uint32_t lensum = m + n, dist = lensum - 2u * lcs;
+    const double norm_dist = __ddiv_rn((double)dist, (double)lensum);
+    const double norm_sim = __dsub_rn(1.0, norm_dist);
+    return __ddiv_rn(__dmul_rn(norm_sim, 100.0), 100.0);
+}
+
+template <int W, bool LEVELS>
 __global__ void __launch_bounds__(Q_MAX_THREADS, 1)
 qratio_allpairs_kernel(const QratioParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned tid = threadIdx.x, nthr = blockDim.x;
-    const QratioLayout lay = qratio_layout(p.n_alpha, W, nthr, p.tile_left);
+    const QratioLayout lay = qratio_layout(p.n_alpha, W, nthr, p.tile_left, LEVELS);
     uint64_t *s_pm = reinterpret_cast<uint64_t *>(smem_raw + lay.pm);      // [c][w][thread]
     double *s_acc = reinterpret_cast<double *>(smem_raw + lay.acc);        // [li][thread]
     uint8_t *s_chr = smem_raw + lay.chr;
     uint32_t *s_lev_off = reinterpret_cast<uint32_t *>(smem_raw + lay.lev_off);
+    uint32_t *s_lev_len = reinterpret_cast<uint32_t *>(smem_raw + lay.lev_len);
     uint32_t *s_item_g0 = reinterpret_cast<uint32_t *>(smem_raw + lay.item_g0);
     uint64_t *s_cat = reinterpret_cast<uint64_t *>(smem_raw + lay.cat);
-    uint32_t *s_misc = reinterpret_cast<uint32_t *>(smem_raw + lay.misc);  // [0] max K right, [1] max K left
+    uint32_t *s_misc = reinterpret_cast<uint32_t *>(smem_raw + lay.misc);  // [0] max K right
 
     unsigned long long *count = reinterpret_cast<unsigned long long *>(p.job.out_count);
     const bool flat = p.job.flat != 0;
     const double thr = p.job.threshold;
     unsigned long long st_evals = 0;
+    const uint64_t *pm = s_pm + tid;
 
-    const uint32_t n_tiles = p.n_ltiles * p.n_rtiles;
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint32_t lt = tile / p.n_rtiles, rt = tile - lt * p.n_rtiles;
-        const uint32_t l0 = p.job.l_row_begin + lt * p.tile_left;
-        const uint32_t nl = min(p.tile_left, p.job.l_row_end - l0);
-        const uint32_t G0 = __ldg(p.L.item_level_off + l0);
-        const uint32_t nlev = __ldg(p.L.item_level_off + l0 + nl) - G0;
-        const uint32_t C0 = __ldg(p.L.level_chr_off + G0);
-        const uint32_t nchr = __ldg(p.L.level_chr_off + G0 + nlev) - C0;
+    // (re)build my pattern masks for right level g; returns its length
+    auto build_masks = [&](uint32_t g) {
+        const uint32_t c0 = __ldg(p.R.level_chr_off + g), m = __ldg(p.R.level_len + g);
+        for (uint32_t row = 0; row < p.n_alpha * W; ++row) s_pm[(size_t)row * nthr + tid] = 0;
+        for (uint32_t j = 0; j < m; j += 8) {
+            const uint64_t w8 = __ldg(reinterpret_cast<const uint64_t *>(p.R.chr + c0 + j));
+            for (uint32_t q = 0; q < 8 && j + q < m; ++q) {
+                const uint32_t c = (uint32_t)(w8 >> (8 * q)) & 0xffu;
+                s_pm[((size_t)c * W + ((j + q) >> 6)) * nthr + tid] |= 1ull << ((j + q) & 63u);
+            }
+        }
+        return m;
+    };
 
-        __syncthreads();  // previous tile fully consumed
-        for (uint32_t i = tid; i < nchr; i += nthr) s_chr[i] = __ldg(p.L.chr + C0 + i);
-        for (uint32_t g = tid; g <= nlev; g += nthr) s_lev_off[g] = __ldg(p.L.level_chr_off + G0 + g) - C0;
-        if (tid <= nl) s_item_g0[tid] = __ldg(p.L.item_level_off + l0 + tid) - G0;
-        if (tid < nl) s_cat[tid] = p.job.cat_mode ? __ldg(p.job.l_cat + l0 + tid) : 0;
-        if (tid < 2) s_misc[tid] = 0;
-        __syncthreads();
-
-        const uint32_t r = rt * nthr + tid;
-        const bool r_valid = r < p.R.n_items;
+    const uint32_t n_units = p.n_lgroups * p.n_rblocks;
+    for (uint32_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const uint32_t rb = unit / p.n_lgroups, lgroup = unit - rb * p.n_lgroups;
+        const uint32_t r = p.r_begin + rb * nthr + tid;
+        const bool r_valid = r < p.r_end;
         uint32_t rg0 = 0, kr = 0;
         uint64_t rcat = 0;
         if (r_valid) {
@@ -104,103 +165,137 @@ qratio_allpairs_kernel(const QratioParams p) {
             kr = __ldg(p.R.item_level_off + r + 1) - rg0;
             if (p.job.cat_mode) rcat = __ldg(p.job.r_cat + r);
         }
-        {   // tile-wide level counts bound the schedule
+        uint32_t cur_slot = 0xffffffffu, m = 0;
+        if (!LEVELS && kr) { m = build_masks(rg0); cur_slot = 0; }  // my columns only: no barrier needed
+        if (LEVELS) {
+            __syncthreads();  // s_misc of the previous unit consumed
+            if (tid == 0) s_misc[0] = 0;
+            __syncthreads();
             uint32_t k = kr;
             for (int o = 16; o; o >>= 1) k = max(k, __shfl_xor_sync(FULL_MASK, k, o));
             if ((tid & 31u) == 0) atomicMax(&s_misc[0], k);
-            if (tid < nl) atomicMax(&s_misc[1], s_item_g0[tid + 1] - s_item_g0[tid]);
-        }
-        for (uint32_t li = 0; li < nl; ++li) s_acc[li * nthr + tid] = 0.0;
-        __syncthreads();
-        const uint32_t max_kr = s_misc[0], max_kl = s_misc[1];
-        const uint32_t t_end = flat ? 1u : max(max_kr, max_kl);
-
-        uint32_t cur_slot = 0xffffffffu, m = 0;
-        double w = flat ? 2.0 : 1.0;
-        for (uint32_t t = 1; t <= t_end; ++t) {
-            w *= 0.5;
-            if (kr) {
-                const uint32_t slot = flat ? 0u : min(t, kr - 1);
-                if (slot != cur_slot) {  // (re)build my pattern masks for this right level
-                    cur_slot = slot;
-                    const uint32_t c0 = __ldg(p.R.level_chr_off + rg0 + slot);
-                    m = __ldg(p.R.level_chr_off + rg0 + slot + 1) - c0;
-                    for (uint32_t row = 0; row < p.n_alpha * W; ++row) s_pm[row * nthr + tid] = 0;
-                    for (uint32_t j = 0; j < m; ++j) {
-                        const uint32_t c = __ldg(p.R.chr + c0 + j);
-                        s_pm[(c * W + (j >> 6)) * nthr + tid] |= 1ull << (j & 63u);
-                    }
-                }
-            }
-            for (uint32_t li = 0; li < nl; ++li) {
-                const uint32_t lg0 = s_item_g0[li], kl = s_item_g0[li + 1] - lg0;
-                if (kl == 0 || t > max(kl, max_kr)) continue;  // uniform: nobody needs this step
-                const uint32_t gl = lg0 + (flat ? 0u : min(t, kl - 1));
-                const uint32_t tb = s_lev_off[gl], n = s_lev_off[gl + 1] - tb;
-                uint64_t S[W];
-#pragma unroll
-                for (int x = 0; x < W; ++x) S[x] = ~0ull;
-                const uint64_t *pm = s_pm + tid;
-                for (uint32_t j = 0; j < n; ++j) {
-                    const uint32_t c = s_chr[tb + j];
-                    const uint64_t *row = pm + (size_t)c * W * nthr;
-                    uint32_t carry = 0;
-#pragma unroll
-                    for (int x = 0; x < W; ++x) {
-                        const uint64_t M = row[(size_t)x * nthr];
-                        const uint64_t u = S[x] & M;
-                        const uint64_t sum = S[x] + u;
-                        const uint64_t sum2 = sum + carry;
-                        if (W > 1) carry = (sum < u) | (sum2 < sum);
-                        S[x] = sum2 | (S[x] - u);
-                    }
-                }
-                const bool active = r_valid && kr && (flat || t <= max(kl, kr));
-                if (active) {
-                    uint32_t lcs = 0;
-#pragma unroll
-                    for (int x = 0; x < W; ++x) lcs += __popcll(~S[x]);
-                    double ratio = 0.0;  // QRatio is 0 when either processed string is empty
-                    if (m && n) {
-                        const uint32_t lensum = m + n, dist = lensum - 2u * lcs;
-                        const double norm_dist = __ddiv_rn((double)dist, (double)lensum);
-                        const double norm_sim = __dsub_rn(1.0, norm_dist);
-                        ratio = __ddiv_rn(__dmul_rn(norm_sim, 100.0), 100.0);
-                    }
-                    double *a = s_acc + li * nthr + tid;
-                    *a = __fma_rn(ratio, w, *a);
-                    ++st_evals;
-                }
-            }
         }
 
-        for (uint32_t li = 0; li < nl; ++li) {
-            const uint32_t kl = s_item_g0[li + 1] - s_item_g0[li];
-            bool ok = r_valid && keep_categories(p.job.cat_mode, s_cat[li], rcat);
-            if (ok && (kl == 0) != (kr == 0)) {  // IndexError in the reference
-                atomicOr(p.job.out_flags, NSM_FLAG_EMPTY_ITEM);
-                ok = false;
+        const uint32_t lt_begin = lgroup * Q_GROUP;
+        const uint32_t lt_end = min(lt_begin + (uint32_t)Q_GROUP, p.n_ltiles);
+        for (uint32_t lt = lt_begin; lt < lt_end; ++lt) {
+            const uint32_t l0 = p.job.l_row_begin + lt * p.tile_left;
+            const uint32_t nl = min(p.tile_left, p.job.l_row_end - l0);
+            const uint32_t G0 = __ldg(p.L.item_level_off + l0);
+            const uint32_t nlev = __ldg(p.L.item_level_off + l0 + nl) - G0;
+            uint32_t C0 = 0, nchr = 0;
+            if (nlev) {
+                C0 = __ldg(p.L.level_chr_off + G0);
+                nchr = __ldg(p.L.level_chr_off + G0 + nlev - 1) +
+                       ((__ldg(p.L.level_len + G0 + nlev - 1) + 7u) & ~7u) - C0;
             }
-            const double score = s_acc[li * nthr + tid];
-            emit_pairs(ok && score >= thr, l0 + li, r, score, p.job.out_pairs, p.job.out_capacity,
-                       count, p.job.out_flags);
+
+            __syncthreads();  // previous tile fully consumed
+            for (uint32_t i = tid; i < nchr / 8; i += nthr)
+                reinterpret_cast<uint64_t *>(s_chr)[i] =
+                    __ldg(reinterpret_cast<const uint64_t *>(p.L.chr + C0) + i);
+            for (uint32_t g = tid; g < nlev; g += nthr) {
+                s_lev_off[g] = __ldg(p.L.level_chr_off + G0 + g) - C0;
+                s_lev_len[g] = __ldg(p.L.level_len + G0 + g);
+            }
+            if (tid <= nl) s_item_g0[tid] = __ldg(p.L.item_level_off + l0 + tid) - G0;
+            if (tid < nl) s_cat[tid] = p.job.cat_mode ? __ldg(p.job.l_cat + l0 + tid) : 0;
+            __syncthreads();
+
+            if (!LEVELS) {
+                // ---- one level per item: score and emit pair by pair ------------------------
+                for (uint32_t li = 0; li < nl; ++li) {
+                    const uint32_t lg0 = s_item_g0[li], kl = s_item_g0[li + 1] - lg0;
+                    bool ok = r_valid && keep_categories(p.job.cat_mode, s_cat[li], rcat);
+                    double score = 0.0;
+                    if (kl) {  // uniform; threads without a right level compute on stale masks, unused
+                        const uint32_t n = s_lev_len[lg0];
+                        const uint32_t lcs = lcs_bitparallel<W>(pm, nthr, s_chr + s_lev_off[lg0], n);
+                        if (kr) {
+                            // flat: score_func(l0, r0); else compare_terms on K = 1 items: t = 1, weight 1/2
+                            score = qratio_from_lcs(m, n, lcs);
+                            if (!flat) score = __fma_rn(score, 0.5, 0.0);
+                            ++st_evals;
+                        }
+                    }
+                    if (ok && (kl == 0) != (kr == 0)) {  // IndexError in the reference
+                        atomicOr(p.job.out_flags, NSM_FLAG_EMPTY_ITEM);
+                        ok = false;
+                    }
+                    emit_pairs(ok && score >= thr, l0 + li, r, score, p.job.out_pairs,
+                               p.job.out_capacity, count, p.job.out_flags);
+                }
+            } else {
+                // ---- compare_terms' schedule as the outer loop, partial scores in smem --------
+                for (uint32_t li = 0; li < nl; ++li) s_acc[(size_t)li * nthr + tid] = 0.0;
+                uint32_t max_kl = 0;
+                for (uint32_t li = 0; li < nl; ++li) max_kl = max(max_kl, s_item_g0[li + 1] - s_item_g0[li]);
+                const uint32_t max_kr = s_misc[0];
+                const uint32_t t_end = max(max_kr, max_kl);
+                double w = 1.0;
+                for (uint32_t t = 1; t <= t_end; ++t) {
+                    w *= 0.5;
+                    if (kr) {
+                        const uint32_t slot = min(t, kr - 1);
+                        if (slot != cur_slot) { cur_slot = slot; m = build_masks(rg0 + slot); }
+                    }
+                    for (uint32_t li = 0; li < nl; ++li) {
+                        const uint32_t lg0 = s_item_g0[li], kl = s_item_g0[li + 1] - lg0;
+                        if (kl == 0 || t > max(kl, max_kr)) continue;  // uniform: nobody needs this step
+                        const uint32_t gl = lg0 + min(t, kl - 1);
+                        const uint32_t n = s_lev_len[gl];
+                        const uint32_t lcs = lcs_bitparallel<W>(pm, nthr, s_chr + s_lev_off[gl], n);
+                        if (r_valid && kr && t <= max(kl, kr)) {
+                            double *a = s_acc + (size_t)li * nthr + tid;
+                            *a = __fma_rn(qratio_from_lcs(m, n, lcs), w, *a);
+                            ++st_evals;
+                        }
+                    }
+                }
+                cur_slot = 0xffffffffu;  // the next tile starts over at step 1
+                for (uint32_t li = 0; li < nl; ++li) {
+                    const uint32_t kl = s_item_g0[li + 1] - s_item_g0[li];
+                    bool ok = r_valid && keep_categories(p.job.cat_mode, s_cat[li], rcat);
+                    if (ok && (kl == 0) != (kr == 0)) {  // IndexError in the reference
+                        atomicOr(p.job.out_flags, NSM_FLAG_EMPTY_ITEM);
+                        ok = false;
+                    }
+                    const double score = s_acc[(size_t)li * nthr + tid];
+                    emit_pairs(ok && score >= thr, l0 + li, r, score, p.job.out_pairs,
+                               p.job.out_capacity, count, p.job.out_flags);
+                }
+            }
         }
     }
-    if (p.job.out_stats && st_evals) {
+    if (p.job.out_stats) {
         for (int o = 16; o; o >>= 1) st_evals += __shfl_xor_sync(FULL_MASK, st_evals, o);
-        if ((tid & 31u) == 0)
+        if ((tid & 31u) == 0 && st_evals)
             atomicAdd(reinterpret_cast<unsigned long long *>(p.job.out_stats) + NSM_STAT_LEVEL_EVALS,
                       st_evals);
     }
 }
 
-template <int W>
+template <int W, bool LEVELS>
 static int launch_qratio(const QratioParams &p, size_t smem, uint32_t grid, cudaStream_t stream) {
-    NSM_CUDA_CHECK(cudaFuncSetAttribute(qratio_allpairs_kernel<W>,
+    NSM_CUDA_CHECK(cudaFuncSetAttribute(qratio_allpairs_kernel<W, LEVELS>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    qratio_allpairs_kernel<W><<<grid, p.threads, smem, stream>>>(p);
+    qratio_allpairs_kernel<W, LEVELS><<<grid, p.threads, smem, stream>>>(p);
+    count_launch();
     NSM_CUDA_CHECK(cudaGetLastError());
     return NSM_OK;
+}
+
+template <bool LEVELS>
+static int dispatch_qratio(uint32_t words, const QratioParams &p, size_t smem, uint32_t grid,
+                           cudaStream_t stream) {
+    switch (words) {
+        case 1: return launch_qratio<1, LEVELS>(p, smem, grid, stream);
+        case 2: return launch_qratio<2, LEVELS>(p, smem, grid, stream);
+        case 3: return launch_qratio<3, LEVELS>(p, smem, grid, stream);
+        case 4: return launch_qratio<4, LEVELS>(p, smem, grid, stream);
+        case 6: return launch_qratio<6, LEVELS>(p, smem, grid, stream);
+        default: return launch_qratio<8, LEVELS>(p, smem, grid, stream);
+    }
 }
 
 }  // namespace nsm
@@ -220,15 +315,15 @@ extern "C" int nsm_qratio_allpairs(const nsm_strings_t *left, const nsm_strings_
         set_error("both sides must be packed with one alphabet of <= 255 codes");
         return NSM_ERR_BAD_ARG;
     }
-    const uint32_t words = (right->max_len + 63) / 64 ? (right->max_len + 63) / 64 : 1;
-    if (words > (uint32_t)Q_MAX_WORDS) {
+    if (right->class_end[Q_MAX_WORDS - 1] != right->n_items) {
         set_error("right level strings of up to %u characters; the kernel handles %d",
                   right->max_len, 64 * Q_MAX_WORDS);
         return NSM_ERR_UNSUPPORTED;
     }
+    const bool levels = left->max_levels > 1 || right->max_levels > 1;
     const uint32_t kl = left->max_levels ? left->max_levels : 1u;
-    const uint32_t per_item_chr = kl * (left->max_len ? left->max_len : 1u);
-    uint32_t tl = (uint32_t)Q_TILE_LEFT;
+    const uint32_t per_item_chr = kl * (((left->max_len ? left->max_len : 1u) + 7u) & ~7u);
+    uint32_t tl = levels ? (uint32_t)Q_TILE_LEVELS : (uint32_t)Q_TILE_FLAT;
     if (per_item_chr * tl > (uint32_t)Q_CHR_CAP) tl = (uint32_t)Q_CHR_CAP / per_item_chr;
     if (kl * tl > (uint32_t)Q_LEV_CAP) tl = (uint32_t)Q_LEV_CAP / kl;
     if (tl == 0) {
@@ -240,33 +335,44 @@ extern "C" int nsm_qratio_allpairs(const nsm_strings_t *left, const nsm_strings_
     p.L = *left; p.R = *right; p.job = *job;
     p.tile_left = tl;
     p.n_alpha = left->n_alphabet ? left->n_alphabet : 1u;
-    // words actually instantiated: 1, 2, 3, 4, 6, 8
-    const uint32_t w_inst = words <= 4 ? words : (words <= 6 ? 6u : 8u);
-    uint32_t threads = Q_MAX_THREADS;
-    while (threads >= 32 && qratio_layout(p.n_alpha, w_inst, threads, tl).total > Q_SMEM_BUDGET)
-        threads -= 32;
-    if (threads < 32) {
-        set_error("alphabet %u x %u words does not fit shared memory", p.n_alpha, w_inst);
-        return NSM_ERR_UNSUPPORTED;
-    }
-    p.threads = threads;
-    const size_t smem = qratio_layout(p.n_alpha, w_inst, threads, tl).total;
     const uint32_t n_rows = job->l_row_end - job->l_row_begin;
     p.n_ltiles = (n_rows + tl - 1) / tl;
-    p.n_rtiles = (right->n_items + threads - 1) / threads;
-    const uint64_t n_tiles64 = (uint64_t)p.n_ltiles * p.n_rtiles;
-    if (n_tiles64 > 0xffffffffull) {
-        set_error("too many tiles (%llu); split the left row block", (unsigned long long)n_tiles64);
-        return NSM_ERR_UNSUPPORTED;
+    p.n_lgroups = (p.n_ltiles + Q_GROUP - 1) / Q_GROUP;
+
+    // one launch per word-count class of the right side (its items are stored class by class),
+    // each with the narrowest bit-vectors and as many threads as its mask tables leave room for
+    for (uint32_t w = 0; w < (uint32_t)Q_MAX_WORDS; ++w) {
+        p.r_begin = w ? right->class_end[w - 1] : 0u;
+        p.r_end = right->class_end[w];
+        if (p.r_end <= p.r_begin) continue;
+        const uint32_t words = w + 1;
+        // words actually instantiated: 1, 2, 3, 4, 6, 8
+        const uint32_t w_inst = words <= 4 ? words : (words <= 6 ? 6u : 8u);
+        uint32_t threads = Q_MAX_THREADS;
+        while (threads >= 32 && qratio_layout(p.n_alpha, w_inst, threads, tl, levels).total > Q_SMEM_BUDGET)
+            threads -= 32;
+        if (threads < 32) {
+            set_error("alphabet %u x %u words does not fit shared memory", p.n_alpha, w_inst);
+            return NSM_ERR_UNSUPPORTED;
+        }
+        // no more threads than right items (rounded up to a warp): a small right side, e.g. one
+        // term against many synonyms, should not pay for idle mask columns
+        const uint32_t n_right = p.r_end - p.r_begin;
+        const uint32_t need = ((n_right + 31u) / 32u) * 32u;
+        if (threads > need) threads = need;
+        p.threads = threads;
+        const size_t smem = qratio_layout(p.n_alpha, w_inst, threads, tl, levels).total;
+        p.n_rblocks = (n_right + threads - 1) / threads;
+        const uint64_t n_units = (uint64_t)p.n_lgroups * p.n_rblocks;
+        if (n_units > 0xffffffffull) {
+            set_error("too many work units (%llu); split the left row block", (unsigned long long)n_units);
+            return NSM_ERR_UNSUPPORTED;
+        }
+        const uint32_t resident = (uint32_t)sm_count();
+        const uint32_t grid = (uint32_t)(n_units < resident ? n_units : resident);
+        const int rc = levels ? dispatch_qratio<true>(w_inst, p, smem, grid, stream)
+                              : dispatch_qratio<false>(w_inst, p, smem, grid, stream);
+        if (rc) return rc;
     }
-    const uint32_t resident = (uint32_t)sm_count();
-    const uint32_t grid = (uint32_t)(n_tiles64 < resident ? n_tiles64 : resident);
-    switch (w_inst) {
-        case 1: return launch_qratio<1>(p, smem, grid, stream);
-        case 2: return launch_qratio<2>(p, smem, grid, stream);
-        case 3: return launch_qratio<3>(p, smem, grid, stream);
-        case 4: return launch_qratio<4>(p, smem, grid, stream);
-        case 6: return launch_qratio<6>(p, smem, grid, stream);
-        default: return launch_qratio<8>(p, smem, grid, stream);
-    }
+    return NSM_OK;
 }

@@ -38,6 +38,7 @@ class DeviceCohort:
     max_levels: int
     h2d_bytes: int
     weights: np.ndarray             # per-item work estimate, for row-block balancing
+    perm: Optional[np.ndarray] = None  # stored position -> caller's item index (strings)
 
 
 @dataclass
@@ -84,7 +85,7 @@ class Engine:
         if isinstance(packed, PackedSets):
             return packed.arrays()
         if isinstance(packed, PackedStrings):
-            return [packed.item_level_off, packed.level_chr_off, packed.chr]
+            return packed.arrays()
         raise TypeError(type(packed))
 
     def pin(self, packed) -> List[torch.Tensor]:
@@ -108,7 +109,8 @@ class Engine:
         else:
             st = nsmlib.NsmStrings(*[t.data_ptr() for t in tensors], packed.n_items,
                                    packed.n_levels, packed.max_levels, packed.max_len,
-                                   packed.n_alphabet)
+                                   packed.n_alphabet, 0,
+                                   (C.c_uint32 * 8)(*[int(x) for x in packed.classes()]))
             per_level = packed.level_lengths()
             kind = "strings"
         # per-item work estimate (sum of level sizes + 1), used to balance row blocks over GPUs
@@ -116,7 +118,7 @@ class Engine:
         off = packed.item_level_off.astype(np.int64)
         per_item = (csum[off[1:]] - csum[off[:-1]]).astype(np.float64) + 1.0
         return DeviceCohort(kind, st, tensors, packed.n_items, packed.max_levels,
-                            sum(a.nbytes for a in arrays), per_item)
+                            sum(a.nbytes for a in arrays), per_item, getattr(packed, "perm", None))
 
     def upload_masks(self, masks: Optional[np.ndarray]) -> Optional[torch.Tensor]:
         if masks is None:
@@ -205,7 +207,7 @@ class Engine:
             if self.time_kernels:
                 e1.record(stream)
                 self._timed.append((e0, e1))
-            self.launches += 1
+            self.launches += self.lib.nsm_last_launch_count()
             ctl_pin[slot].copy_(c, non_blocking=True)
             done = torch.cuda.Event()
             done.record(stream)
@@ -303,7 +305,13 @@ class Engine:
             # the parts of one job are adjacent in the pinned arena
             lo, hi = parts[0][0], parts[-1][0] + parts[-1][1]
             view = pin[lo:hi].numpy().view(PAIR_DTYPE)
-            outs.append(view.copy() if copy else view)
+            out = view.copy() if copy else view
+            job = jobs[len(outs)]
+            if job.left.perm is not None:   # stored positions -> the caller's item indices
+                out["left"] = job.left.perm[out["left"]]
+            if job.right.perm is not None:
+                out["right"] = job.right.perm[out["right"]]
+            outs.append(out)
         return outs
 
     # ------------------------------------------------------------------ roofline denominators

@@ -19,8 +19,8 @@ STAT_NAMES = ("candidates", "level_evals", "level_merges", "bound_pairs")
 PAIR_DTYPE = np.dtype([("left", np.uint32), ("right", np.uint32), ("score", np.float64)])
 assert PAIR_DTYPE.itemsize == 16
 
-EXPORTS = ("nsm_version", "nsm_last_error", "nsm_jaccard_allpairs", "nsm_qratio_allpairs",
-           "nsm_microbench")
+EXPORTS = ("nsm_version", "nsm_last_error", "nsm_last_launch_count", "nsm_jaccard_allpairs",
+           "nsm_qratio_allpairs", "nsm_microbench")
 
 
 class NsmSets(C.Structure):
@@ -33,8 +33,10 @@ class NsmSets(C.Structure):
 
 class NsmStrings(C.Structure):
     _fields_ = [("item_level_off", C.c_void_p), ("level_chr_off", C.c_void_p),
-                ("chr", C.c_void_p), ("n_items", C.c_uint32), ("n_levels", C.c_uint32),
-                ("max_levels", C.c_uint32), ("max_len", C.c_uint32), ("n_alphabet", C.c_uint32)]
+                ("level_len", C.c_void_p), ("chr", C.c_void_p), ("n_items", C.c_uint32),
+                ("n_levels", C.c_uint32), ("max_levels", C.c_uint32), ("max_len", C.c_uint32),
+                ("n_alphabet", C.c_uint32), ("reserved_", C.c_uint32),
+                ("class_end", C.c_uint32 * 8)]
 
 
 class NsmJob(C.Structure):
@@ -63,6 +65,7 @@ def load() -> C.CDLL:
     lib = C.CDLL(str(LIB_PATH))
     lib.nsm_version.restype = C.c_int
     lib.nsm_last_error.restype = C.c_char_p
+    lib.nsm_last_launch_count.restype = C.c_int
     for name, first in (("nsm_jaccard_allpairs", NsmSets), ("nsm_qratio_allpairs", NsmStrings)):
         fn = getattr(lib, name)
         fn.restype = C.c_int

@@ -33,8 +33,14 @@ fuzzy_match operands (``PackedStrings``): per level the string ``fuzzy_match`` w
 code point through an alphabet shared by both sides:
 
     item_level_off  uint32[n_items+1]
-    level_chr_off   uint32[n_levels+1]
-    chr             uint8[n_chr]        dense alphabet codes (0 .. n_alphabet-1)
+    level_chr_off   uint32[n_levels]    start of the level's string in chr, a multiple of 8
+    level_len       uint32[n_levels]    its length in code points
+    chr             uint8[n_chr]        dense alphabet codes (0 .. n_alphabet-1), every string
+                                        padded to a multiple of 8 bytes (the kernel reads 8 at a time)
+
+Items are stored ordered by the number of 64-bit words their longest level string needs
+(``class_end[w]`` = end of the items needing <= w+1 words), so that the kernel can run every class
+with the narrowest bit-vectors; ``perm`` maps a stored position back to the caller's item index.
 """
 from __future__ import annotations
 
@@ -117,10 +123,13 @@ class PackedSets:
 class PackedStrings:
     item_level_off: np.ndarray
     level_chr_off: np.ndarray
+    level_len: np.ndarray
     chr: np.ndarray
     n_alphabet: int
     max_levels: int = 0
     max_len: int = 0
+    perm: np.ndarray | None = None          # stored position -> original item index
+    class_end: np.ndarray | None = None     # uint32[8]
 
     @property
     def n_items(self) -> int:
@@ -128,24 +137,46 @@ class PackedStrings:
 
     @property
     def n_levels(self) -> int:
-        return len(self.level_chr_off) - 1
+        return len(self.level_len)
+
+    def classes(self) -> np.ndarray:
+        if self.class_end is not None:
+            return self.class_end
+        return np.full(WORD_CLASSES, self.n_items, dtype=np.uint32)
+
+    def arrays(self):
+        return [self.item_level_off, self.level_chr_off, self.level_len, self.chr]
 
     def level_lengths(self) -> np.ndarray:
-        return np.diff(self.level_chr_off.astype(np.int64))
+        return self.level_len.astype(np.int64)
 
     def levels_per_item(self) -> np.ndarray:
         return np.diff(self.item_level_off.astype(np.int64))
 
     def nbytes(self) -> int:
-        return self.item_level_off.nbytes + self.level_chr_off.nbytes + self.chr.nbytes
+        return sum(a.nbytes for a in self.arrays())
+
+    def level_string_codes(self, g: int) -> np.ndarray:
+        o = int(self.level_chr_off[g])
+        return self.chr[o : o + int(self.level_len[g])]
 
     def rows(self, begin: int, end: int) -> "PackedStrings":
         g0, g1 = int(self.item_level_off[begin]), int(self.item_level_off[end])
-        c0, c1 = int(self.level_chr_off[g0]), int(self.level_chr_off[g1])
+        c0 = int(self.level_chr_off[g0]) if g1 > g0 else 0
+        c1 = int(self.level_chr_off[g1 - 1]) + _pad8(int(self.level_len[g1 - 1])) if g1 > g0 else 0
+        cls = np.clip(self.classes().astype(np.int64) - begin, 0, end - begin).astype(np.uint32)
         return PackedStrings(
             (self.item_level_off[begin : end + 1] - np.uint32(g0)).astype(np.uint32),
-            (self.level_chr_off[g0 : g1 + 1] - np.uint32(c0)).astype(np.uint32),
-            self.chr[c0:c1].copy(), self.n_alphabet, self.max_levels, self.max_len)
+            (self.level_chr_off[g0:g1] - np.uint32(c0)).astype(np.uint32),
+            self.level_len[g0:g1].copy(), self.chr[c0:c1].copy(), self.n_alphabet, self.max_levels,
+            self.max_len, None if self.perm is None else self.perm[begin:end].copy(), cls)
+
+
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+WORD_CLASSES = 8   # 64-bit words per pattern the kernel instantiates: up to 512 characters
 
 
 # ------------------------------------------------------------------------------------------
@@ -383,24 +414,40 @@ def pack_strings(*sides: Sequence[Sequence[str]]) -> List[PackedStrings]:
     per_side = []
     for s in sides:
         k = np.fromiter((len(lv) for lv in s), dtype=np.int64, count=len(s))
-        strs = [x for lv in s for x in lv]
+        # order items by the 64-bit words their longest level needs (stable)
+        longest = np.fromiter((max((len(x) for x in lv), default=0) for lv in s), dtype=np.int64,
+                              count=len(s))
+        words = np.minimum(np.maximum((longest + 63) // 64, 1), WORD_CLASSES + 1)
+        perm = np.argsort(words, kind="stable")
+        class_end = np.searchsorted(words[perm], np.arange(1, WORD_CLASSES + 1), side="right")
+        strs = [x for i in perm for x in s[i]]
         lens = np.fromiter((len(x) for x in strs), dtype=np.int64, count=len(strs))
         cps = np.frombuffer("".join(strs).encode("utf-32-le"), dtype=np.uint32)
-        per_side.append((k, lens, cps))
-    alphabet = np.unique(np.concatenate([c for _, _, c in per_side])) if per_side else np.zeros(0)
+        per_side.append((k[perm], lens, cps, perm, class_end))
+    alphabet = np.unique(np.concatenate([c[2] for c in per_side])) if per_side else np.zeros(0)
     if len(alphabet) > MAX_ALPHABET:
         raise PackError(f"{len(alphabet)} distinct code points; the packed format allows 255")
     out = []
-    for k, lens, cps in per_side:
+    for k, lens, cps, perm, class_end in per_side:
         item_level_off = np.zeros(len(k) + 1, dtype=np.int64)
         np.cumsum(k, out=item_level_off[1:])
+        padded = _pad8(lens)
         level_chr_off = np.zeros(len(lens) + 1, dtype=np.int64)
-        np.cumsum(lens, out=level_chr_off[1:])
+        np.cumsum(padded, out=level_chr_off[1:])
+        if level_chr_off[-1] >= 2 ** 32:
+            raise PackError("more than 4 GiB of level strings on one side")
         codes = np.searchsorted(alphabet, cps).astype(np.uint8)
-        out.append(PackedStrings(item_level_off.astype(np.uint32), level_chr_off.astype(np.uint32),
-                                 np.ascontiguousarray(codes), int(len(alphabet)),
+        chr_ = np.zeros(int(level_chr_off[-1]), dtype=np.uint8)
+        if len(codes):
+            src_off = np.zeros(len(lens) + 1, dtype=np.int64)
+            np.cumsum(lens, out=src_off[1:])
+            dest = np.repeat(level_chr_off[:-1] - src_off[:-1], lens) + np.arange(len(codes), dtype=np.int64)
+            chr_[dest] = codes
+        out.append(PackedStrings(item_level_off.astype(np.uint32), level_chr_off[:-1].astype(np.uint32),
+                                 lens.astype(np.uint32), chr_, int(len(alphabet)),
                                  int(k.max()) if len(k) else 0,
-                                 int(lens.max()) if len(lens) else 0))
+                                 int(lens.max()) if len(lens) else 0,
+                                 perm.astype(np.uint32), class_end.astype(np.uint32)))
     return out
 
 

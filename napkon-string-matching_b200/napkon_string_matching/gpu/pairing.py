@@ -183,8 +183,12 @@ def score_all_pairs(left_levels, right_levels, score_func: str, score_threshold:
     dl, dr = engine.upload(pl), engine.upload(pr)
     kw = {}
     if categories is not None and host_cat is None:
-        kw = dict(l_cat=engine.upload_masks(categories["left"]),
-                  r_cat=engine.upload_masks(categories["right"]), cat_mode=categories["cat_mode"])
+        # masks are indexed by stored position (string packs group their items by length class)
+        lmask, rmask = categories["left"], categories["right"]
+        if getattr(pl, "perm", None) is not None:
+            lmask, rmask = lmask[pl.perm], rmask[pr.perm]
+        kw = dict(l_cat=engine.upload_masks(lmask), r_cat=engine.upload_masks(rmask),
+                  cat_mode=categories["cat_mode"])
     records = distributed.sharded_all_pairs(
         lambda b, e: engine.all_pairs(dl, dr, score_threshold, rows=(b, e), **kw),
         dl.weights)

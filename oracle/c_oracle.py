@@ -16,8 +16,9 @@ FLAG_ZERO_UNION, FLAG_INDEX_ERROR = 1, 2
 
 
 class _Side(C.Structure):
-    _fields_ = [("item_level_off", C.c_void_p), ("level_off", C.c_void_p), ("tok", C.c_void_p),
-                ("chr", C.c_void_p), ("n_items", C.c_uint32)]
+    _fields_ = [("item_level_off", C.c_void_p), ("level_off", C.c_void_p),
+                ("level_len", C.c_void_p), ("tok", C.c_void_p), ("chr", C.c_void_p),
+                ("n_items", C.c_uint32)]
 
 
 def _lib():
@@ -45,9 +46,10 @@ def _side(p):
         return a.ctypes.data
 
     if hasattr(p, "tok"):
-        s = _Side(ptr(p.item_level_off), ptr(p.level_tok_off), ptr(p.tok), None, p.n_items)
+        s = _Side(ptr(p.item_level_off), ptr(p.level_tok_off), None, ptr(p.tok), None, p.n_items)
     else:
-        s = _Side(ptr(p.item_level_off), ptr(p.level_chr_off), None, ptr(p.chr), p.n_items)
+        s = _Side(ptr(p.item_level_off), ptr(p.level_chr_off), ptr(p.level_len), None, ptr(p.chr),
+                  p.n_items)
     return s, keep
 
 
@@ -69,6 +71,12 @@ def all_pairs(left, right, threshold, flat=False, l_begin=0, l_end=None, l_cat=N
     out = np.zeros(n, dtype=PAIR_DTYPE)
     if n:
         lib.ora_allpairs(*args, out.ctypes.data, n, C.byref(flags))
+    # packs may store their items in another order (strings are grouped by length class):
+    # report the caller's item indices
+    if getattr(left, "perm", None) is not None:
+        out["left"] = left.perm[out["left"]]
+    if getattr(right, "perm", None) is not None:
+        out["right"] = right.perm[out["right"]]
     return out, flags.value
 
 
@@ -77,8 +85,16 @@ def score_pairs(left, right, li, ri, flat=False):
     func = JACCARD if hasattr(left, "tok") else QRATIO
     ls, k1 = _side(left)
     rs, k2 = _side(right)
-    li = np.ascontiguousarray(li, dtype=np.uint32)
-    ri = np.ascontiguousarray(ri, dtype=np.uint32)
+    def stored(p, idx):  # caller's item index -> stored position
+        idx = np.asarray(idx, dtype=np.int64)
+        if getattr(p, "perm", None) is None:
+            return idx
+        inv = np.empty(len(p.perm), dtype=np.int64)
+        inv[p.perm.astype(np.int64)] = np.arange(len(p.perm))
+        return inv[idx]
+
+    li = np.ascontiguousarray(stored(left, li), dtype=np.uint32)
+    ri = np.ascontiguousarray(stored(right, ri), dtype=np.uint32)
     out = np.zeros(len(li), dtype=np.float64)
     flags = C.c_uint32(0)
     lib.ora_score_pairs(func, int(flat), C.byref(ls), C.byref(rs), li.ctypes.data, ri.ctypes.data,

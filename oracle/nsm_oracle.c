@@ -24,7 +24,8 @@
 
 typedef struct {
     const uint32_t *item_level_off; /* [n_items+1] */
-    const uint32_t *level_off;      /* [n_levels+1] tokens (sets) or characters (strings) */
+    const uint32_t *level_off;      /* sets: [n_levels+1] token ranges; strings: [n_levels] start of each string */
+    const uint32_t *level_len;      /* strings: [n_levels] lengths; sets: NULL */
     const uint32_t *tok;            /* sets: sorted unique ids; strings: unused */
     const uint8_t *chr;             /* strings: alphabet codes; sets: unused */
     uint32_t n_items;
@@ -79,8 +80,8 @@ static uint32_t lcs_dp(const uint8_t *a, uint32_t na, const uint8_t *b, uint32_t
 /* QRatio(a, b) / 100 on processed strings: 0 if either is empty, else
  * ((1.0 - dist/lensum) * 100) / 100 with dist = lensum - 2*LCS */
 static double ora_qratio(const ora_side_t *L, uint32_t gl, const ora_side_t *R, uint32_t gr) {
-    uint32_t la = L->level_off[gl], na = L->level_off[gl + 1] - la;
-    uint32_t lb = R->level_off[gr], nb = R->level_off[gr + 1] - lb;
+    uint32_t la = L->level_off[gl], na = L->level_len[gl];
+    uint32_t lb = R->level_off[gr], nb = R->level_len[gr];
     if (na == 0 || nb == 0) return 0.0;
     uint32_t lcs = lcs_dp(L->chr + la, na, R->chr + lb, nb);
     uint32_t lensum = na + nb, dist = lensum - 2 * lcs;

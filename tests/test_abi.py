@@ -33,7 +33,7 @@ def test_struct_layouts_match_the_header():
     from napkon_string_matching.gpu import lib as nsmlib
 
     assert ctypes.sizeof(nsmlib.NsmSets) == 11 * 8 + 6 * 4
-    assert ctypes.sizeof(nsmlib.NsmStrings) == 3 * 8 + 5 * 4 + 4  # padded to 8
+    assert ctypes.sizeof(nsmlib.NsmStrings) == 4 * 8 + 6 * 4 + 8 * 4
     assert nsmlib.NsmJob.threshold.offset == 16
     assert nsmlib.NsmJob.out_pairs.offset == 40
     assert ctypes.sizeof(nsmlib.NsmJob) == 80

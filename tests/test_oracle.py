@@ -186,5 +186,9 @@ def test_pack_strings_alphabet_and_rows():
     pl, pr = pack.pack_strings([["abc", ""], ["größe 12"]], [["cab"]])
     assert pl.n_alphabet == pr.n_alphabet == len(set("abcgröße 12"))
     assert list(pl.level_lengths()) == [3, 0, 8] and pl.max_len == 8 and pl.max_levels == 2
+    assert list(pl.level_chr_off) == [0, 8, 8] and len(pl.chr) == 16
+    alphabet = sorted(set("abcgröße 12"))
+    assert "".join(alphabet[c] for c in pl.level_string_codes(2)) == "größe 12"
     sub = pl.rows(1, 2)
-    assert sub.n_items == 1 and list(sub.level_lengths()) == [8]
+    assert sub.n_items == 1 and list(sub.level_lengths()) == [8] and list(sub.level_chr_off) == [0]
+    assert "".join(alphabet[c] for c in sub.level_string_codes(0)) == "größe 12"
