@@ -378,17 +378,27 @@ jaccard_allpairs_kernel(const JaccardParams p) {
                 const uint32_t kmax_warp = __reduce_max_sync(FULL_MASK, kmax);
                 double score = 0.0, w = flat ? 2.0 : 1.0;
                 uint32_t pjl = 0xffffffffu, pjr = 0xffffffffu, inter = 0, uni = 1, a = 0, b = 0;
+                // the left summaries come through L2: keep the loads of the next two steps in
+                // flight while the current step is scored
+                const uint32_t kl1 = max(kl, 1u);
+                uint32_t ia1 = 0, ia2 = 0;
+                ulonglong2 A1 = make_ulonglong2(0, 0), A2 = A1;
+                if (kmax_warp >= 1) A1 = left_level(c_l, 1, kl1, ia1);
+                if (kmax_warp >= 2) A2 = left_level(c_l, 2, kl1, ia2);
                 for (uint32_t t = 1; t <= kmax_warp; ++t) {
                     const bool on = t <= kmax;
                     const uint32_t jl = flat ? 0u : min(t, kl - 1), jr = flat ? 0u : min(t, c_kr - 1);
                     bool need = false;
                     uint32_t hl = 0, hr = 0;
+                    const ulonglong2 A = A1;
+                    const uint32_t ia = ia1;
+                    A1 = A2; ia1 = ia2;
+                    if (t + 2 <= kmax_warp) A2 = left_level(c_l, t + 2, kl1, ia2);
                     if (on) {
                         ++st_evals;
                         if (jl != pjl || jr != pjr) {
                             pjl = jl; pjr = jr;
-                            uint32_t ia, ib;
-                            const ulonglong2 A = left_level(c_l, t, kl, ia);
+                            uint32_t ib;
                             const ulonglong2 B = right_level(rc, c_r, t, c_kr, ib);
                             a = ia & 0xffffu; b = ib & 0xffffu;
                             inter = __popcll(A.x & B.x);
@@ -407,13 +417,12 @@ jaccard_allpairs_kernel(const JaccardParams p) {
                         uint32_t off_a = 0, off_b = 0;
                         if (need) {
                             const uint32_t gl = lg0 + jl, gr = rg0 + jr;
+                            // four independent loads, one round trip
+                            const uint64_t t2l = __ldg(p.L.level_tail2 + gl), t2r = __ldg(p.R.level_tail2 + gr);
+                            off_a = __ldg(p.L.level_tok_off + gl) + hl;
+                            off_b = __ldg(p.R.level_tok_off + gr) + hr;
                             // a second, independent signature rules most collisions out
-                            if (__ldg(p.L.level_tail2 + gl) & __ldg(p.R.level_tail2 + gr)) {
-                                off_a = __ldg(p.L.level_tok_off + gl) + hl;
-                                off_b = __ldg(p.R.level_tok_off + gr) + hr;
-                            } else {
-                                need = false;
-                            }
+                            need = (t2l & t2r) != 0;
                         }
                         unsigned todo = __ballot_sync(FULL_MASK, need);
                         while (todo) {
