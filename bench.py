@@ -36,6 +36,11 @@ ROOT = pathlib.Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT / "napkon-string-matching_b200"))
 sys.path.insert(0, str(ROOT))
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the
+# committed `ncu --set full` captures (profiles/r1_v9_jaccard_tokenids50k.txt,
+# profiles/r1_v9_jaccard_term200k.txt, profiles/r1_qratio_v2_fuzzy20k.txt); other workloads: null
+NCU_DRAM_BYTES_PER_LAUNCH = {"tokenids50k": 2.2035e9, "term200k": 4.06e7, "fuzzy20k": 2.3e6}
+
 METRIC = "item pair-scores/sec (scored+thresholded)"
 UNIT = "pair-scores/s"
 
@@ -444,7 +449,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                              % (in_bytes / 1e6, 16e-6 * kept)},
             "item_pairs_per_s": item_pairs_step * world / sec_step,
             "roofline": {"bound": "int32_alu", "achieved": achieved / 1e12, "peak": peak_ops / 1e12,
-                         "unit": "Tiop/s", "frac": achieved / peak_ops, "traffic": None,
+                         "unit": "Tiop/s", "frac": achieved / peak_ops,
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.workload),
                          "peak_source": "nsm_microbench measured in this run (LOP3/IADD3 stream)",
                          "alg_ops_per_step": ops_step, "launches_per_step": kernel_launches / args.steps,
                          "kernel_ms_per_launch": kernel_ms / max(1, kernel_launches),
