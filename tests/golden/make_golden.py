@@ -75,6 +75,13 @@ def stage_b(workdir: str) -> None:
                 except Exception as e:  # noqa: BLE001
                     out.append("raises:" + type(e).__name__)
             results[name] = out
+        elif kind == "get_matches":
+            from napkon_string_matching.terminology.mesh import MeshProvider
+
+            provider = MeshProvider(None)
+            provider._synonyms = pd.DataFrame(job["synonyms"])
+            provider._headings = pd.DataFrame(job["synonyms"]).drop_duplicates("Id")
+            results[name] = [provider.get_matches(term, job["score_threshold"]) for term in job["terms"]]
         elif kind == "gen_comp_value":
             results[name] = [ComparableData.gen_comp_value(v) for v in job["values"]]
         elif kind in ("gen_comparable", "compare"):
@@ -116,7 +123,7 @@ def _digest(l_ids, r_ids, scores) -> str:
     return h.hexdigest()
 
 
-def stage_a(full: bool) -> None:
+def stage_a(full: bool, only=None) -> None:
     import numpy as np
 
     sys.path.insert(0, str(PKG))
@@ -162,6 +169,20 @@ def stage_a(full: bool) -> None:
         ["D000001", "D000002", "D000001"], [["Alpha Beta", "Gamma"], "Delta"],
         ["Wie ist der Wert", "und die Summe"],
     ]}
+
+    # -- terminology lookups: MeshProvider.get_matches on a synthetic synonym table
+    rng = np.random.default_rng(77)
+    syn_rows = [("D900001", "Dialyse"), ("D900001", "Renale Dialyse"), ("D900002", "Sonstiges"),
+                ("D900003", "Entlassung"), ("D900003", "Entlassung aus dem Krankenhaus")]
+    for i in range(395):
+        words = [vocab[int(w)] for w in rng.integers(0, 3000, size=int(rng.integers(1, 4)))]
+        syn_rows.append((f"D{int(rng.integers(0, 150)):06d}", " ".join(words)))
+    synonyms = {"Id": [r[0] for r in syn_rows], "Term": [r[1] for r in syn_rows]}
+    terms = [["Dialyse", "nach", "Entlassung"], "Dialyse nach Entlassung",
+             "Hatte Sie Dialyse oder sonstiges?".split(), ["Dialyse"], ["zzz", "qqq"],
+             [vocab[5], vocab[17]], [syn_rows[40][1]], []]
+    jobs["get_matches"] = {"kind": "get_matches", "synonyms": synonyms, "terms": terms,
+                           "score_threshold": 0.3}
 
     # -- gen_comparable runs -------------------------------------------------------------
     def frame(n, seed, name):
@@ -248,6 +269,8 @@ def stage_a(full: bool) -> None:
             "kwargs": dict(score_func="intersection_vs_union", compare_column="Term",
                            score_threshold=0.1, left_name="hap", right_name="pop")}
 
+    if only:
+        jobs = {k: v for k, v in jobs.items() if k in only}
     with tempfile.TemporaryDirectory() as work:
         pickle.dump(jobs, open(os.path.join(work, "jobs.pkl"), "wb"))
         env = dict(os.environ)
@@ -256,6 +279,15 @@ def stage_a(full: bool) -> None:
                        cwd=work)
         results = pickle.load(open(os.path.join(work, "results.pkl"), "rb"))
 
+    if only:
+        if "get_matches" in jobs:
+            gm = jobs["get_matches"]
+            (HERE / "get_matches.json").write_text(json.dumps(
+                {"pinned": False, "synonyms": gm["synonyms"], "score_threshold": gm["score_threshold"],
+                 "cases": [{"term": t, "result": [[i, s, float(v).hex()] for i, s, v in r]}
+                           for t, r in zip(gm["terms"], results["get_matches"])]},
+                indent=1, ensure_ascii=False), encoding="utf-8")
+        return
     scalars = {}
     for name in ("jaccard_hand", "fuzzy_hand", "compare_terms_jaccard", "compare_terms_fuzzy"):
         scalars[name] = {"pinned": "fuzzy" not in name,
@@ -266,6 +298,12 @@ def stage_a(full: bool) -> None:
         for v, r in zip(jobs["gen_comp_value"]["values"], results["gen_comp_value"])]}
     (HERE / "scalar_cases.json").write_text(json.dumps(scalars, indent=1, ensure_ascii=False),
                                             encoding="utf-8")
+    gm = jobs["get_matches"]
+    (HERE / "get_matches.json").write_text(json.dumps(
+        {"pinned": False, "synonyms": gm["synonyms"], "score_threshold": gm["score_threshold"],
+         "cases": [{"term": t, "result": [[i, s, float(v).hex()] for i, s, v in r]}
+                   for t, r in zip(gm["terms"], results["get_matches"])]},
+        indent=1, ensure_ascii=False), encoding="utf-8")
 
     index = json.loads((HERE / "index.json").read_text()) if (HERE / "index.json").exists() else {}
     for name, job in jobs.items():
@@ -313,8 +351,9 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--stage-b", default=None)
     ap.add_argument("--full", action="store_true")
+    ap.add_argument("--only", default=None, help="comma separated job names (others keep their files)")
     a = ap.parse_args()
     if a.stage_b:
         stage_b(a.stage_b)
     else:
-        stage_a(a.full)
+        stage_a(a.full, a.only.split(",") if a.only else None)

@@ -60,3 +60,10 @@ def test_one_against_many_matches_the_scalar_calls(cuda_engine):
     sets = [["a", "b"], ["b"], ["x", "y", "z"], ["a", "b", "c", "d"]]
     many = sf.intersection_vs_union_many(["a", "b", "c"], sets)
     assert list(many) == [2 / 3, 1 / 3, 0.0, 3 / 4]
+
+
+def test_terminology_get_matches_on_the_gpu(cuda_engine):
+    import terminology_cases
+
+    terminology_cases.check_all()
+    terminology_cases.check_add_tokens()

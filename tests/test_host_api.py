@@ -215,3 +215,10 @@ def test_sharded_all_pairs_world_size_2_gloo(tmp_path):
         capture_output=True, text=True, timeout=300, env={**os.environ, "OMP_NUM_THREADS": "2"})
     assert res.returncode == 0, res.stdout + res.stderr
     assert res.stdout.count("ok") == 2, res.stdout
+
+
+def test_terminology_get_matches_host_logic(oracle_engine):
+    import terminology_cases
+
+    terminology_cases.check_all()
+    terminology_cases.check_add_tokens()
