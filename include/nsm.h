@@ -68,14 +68,14 @@ typedef struct nsm_sets {
     const uint32_t *level_info;     /* [n_levels] size | min(n_tail - popc(tail), 255) << 16 */
     const uint64_t *item_any;       /* [n_items][2] OR of (head, tail) over the levels compare_terms uses */
     const uint32_t *item_k;         /* [n_items] number of levels */
-    const uint64_t *slot_ht;        /* [n_slots][n_items][2] (head, tail) of level min(t, K-1), slot t-1 */
-    const uint32_t *slot_info;      /* [n_slots][n_items] level_info of the same level */
+    const uint64_t *slot_ht;        /* [n_slots][slot_stride][2] (head, tail) of level min(t, K-1), slot t-1 */
+    const uint32_t *slot_info;      /* [n_slots][slot_stride] level_info of the same level */
     uint32_t n_items;
     uint32_t n_levels;
     uint32_t max_levels; /* max levels of any item on this side */
     uint32_t n_slots;    /* clamp(max_levels - 1, 1, 10) */
     uint32_t exact_bits; /* 1: vocabulary <= 128 ids, tail bit == id - 64, no token merge needed */
-    uint32_t reserved_;
+    uint32_t slot_stride; /* items per slot row: n_items rounded up to 128, zero-filled */
 } nsm_sets_t;
 
 /* One cohort side for fuzzy_match: per level the processed string QRatio sees

@@ -10,7 +10,8 @@
 // slot-major, so that the data of a block of consecutive items is contiguous per step.
 //
 // Work decomposition: a unit is one block of JT_THREADS right items x J_UNIT_LEFT left items.
-// The right block's slots are staged once per unit in shared memory, one column per thread
+// The right block's slots are staged once per unit in shared memory by TMA bulk copies
+// (cp.async.bulk + mbarrier; rows are padded so a block is one aligned run per step), one column per thread
 // (lane i reads word i: conflict-free), together with one 128-bit "any" word per left item; the
 // left items' slots are read through L1 where a pair needs them.  Each warp then runs a
 // three-stage funnel over its 32 right items x the unit's left items with no block-wide barrier,
@@ -66,6 +67,7 @@ struct __align__(16) JaccardSmem {
     uint32_t qb[J_WARPS][64];
     uint16_t l_k[J_UNIT_LEFT];
     unsigned long long stats[NSM_N_STATS];
+    uint64_t bar;  // mbarrier of the right block's bulk copies
 };
 
 __device__ __forceinline__ float pow2_neg(uint32_t k) {  // 2^-k, 0 when it underflows fp32
@@ -143,6 +145,8 @@ jaccard_allpairs_kernel(const JaccardParams p) {
 
     for (unsigned u = tid; u < J_RCP; u += JT_THREADS) s.rcp_up[u] = u ? __frcp_ru((float)u) : 0.0f;
     if (tid < NSM_N_STATS) s.stats[tid] = 0;
+    if (tid == 0) mbar_init(&s.bar, 1);
+    uint32_t bar_parity = 0;
     unsigned long long st_cand = 0, st_evals = 0, st_merges = 0, st_bound = 0;
     uint32_t out_n = 0;  // warp-uniform fill of s.out[warp]
 
@@ -171,7 +175,7 @@ jaccard_allpairs_kernel(const JaccardParams p) {
             info = __ldg(p.L.level_info + g);
             return make_ulonglong2(__ldg(p.L.level_head + g), __ldg(p.L.level_tail + g));
         }
-        const size_t at = (size_t)(min(t, SL) - 1) * p.L.n_items + item;
+        const size_t at = (size_t)(min(t, SL) - 1) * p.L.slot_stride + item;
         info = __ldg(p.L.slot_info + at);
         return __ldg(l_slot_ht + at);
     };
@@ -194,7 +198,18 @@ jaccard_allpairs_kernel(const JaccardParams p) {
         const uint32_t nl = min((uint32_t)J_UNIT_LEFT, p.job.l_row_end - l0);
 
         __syncthreads();  // previous unit fully consumed
-        // ---- stage my right item's slots: one column per thread ---------------------------
+        // ---- stage the right block's slots: 2 x SR TMA bulk copies, one column per thread ----
+        // (slot rows are padded to 128 items, so every block is a full, 16-byte aligned run)
+        if (tid == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(&s.bar, SR * (JT_THREADS * 16u + JT_THREADS * 4u));
+            for (uint32_t sl = 0; sl < SR; ++sl) {
+                const size_t at = (size_t)sl * p.R.slot_stride + r0;
+                bulk_copy_g2s(&s.r_ht[sl][0], reinterpret_cast<const ulonglong2 *>(p.R.slot_ht) + at,
+                              JT_THREADS * 16u, &s.bar);
+                bulk_copy_g2s(&s.r_info[sl][0], p.R.slot_info + at, JT_THREADS * 4u, &s.bar);
+            }
+        }
         const uint32_t r = r0 + tid;
         const bool r_valid = r < p.R.n_items;
         uint32_t kr = 0;
@@ -202,30 +217,12 @@ jaccard_allpairs_kernel(const JaccardParams p) {
         if (r_valid) {
             kr = __ldg(p.R.item_k + r);
             if (p.job.cat_mode) rcat = __ldg(p.job.r_cat + r);
-        }
-        s.r_k[tid] = kr;
-#pragma unroll
-        for (int sl = 0; sl < J_SLOTS; ++sl) {
-            if ((uint32_t)sl < SR) {
-                ulonglong2 ht = make_ulonglong2(0, 0);
-                uint32_t inf = 0;
-                if (r_valid) {
-                    const size_t at = (size_t)sl * p.R.n_items + r;
-                    ht = __ldg(reinterpret_cast<const ulonglong2 *>(p.R.slot_ht) + at);
-                    inf = __ldg(p.R.slot_info + at);
-                }
-                s.r_ht[sl][tid] = ht;
-                s.r_info[sl][tid] = inf;
-                if ((uint32_t)sl < p.any_depth) { rany_h |= ht.x; rany_t |= ht.y; }
+            if (p.any_depth == 0) {
+                const ulonglong2 any = __ldg(reinterpret_cast<const ulonglong2 *>(p.R.item_any) + r);
+                rany_h = any.x; rany_t = any.y;
             }
         }
-        if (p.any_depth == 0 && r_valid) {
-            const ulonglong2 any = __ldg(reinterpret_cast<const ulonglong2 *>(p.R.item_any) + r);
-            rany_h = any.x; rany_t = any.y;
-        }
-        // threshold <= 0 keeps every pair; an item without levels must reach stage C, which
-        // tells "both empty: score 0" from "one empty: IndexError upstream"
-        if (pass_all || kr == 0) rany_h = rany_t = ~0ull;
+        s.r_k[tid] = kr;
         // ---- the unit's left items: stage A word and level count -------------------------
         for (uint32_t li = tid; li < nl; li += JT_THREADS) {
             const uint32_t k = __ldg(p.L.item_k + l0 + li);
@@ -236,13 +233,23 @@ jaccard_allpairs_kernel(const JaccardParams p) {
                 any = __ldg(reinterpret_cast<const ulonglong2 *>(p.L.item_any) + l0 + li);
             } else {
                 for (uint32_t sl = 0; sl < min(p.any_depth, SL); ++sl) {
-                    const ulonglong2 ht = __ldg(l_slot_ht + (size_t)sl * p.L.n_items + l0 + li);
+                    const ulonglong2 ht = __ldg(l_slot_ht + (size_t)sl * p.L.slot_stride + l0 + li);
                     any.x |= ht.x; any.y |= ht.y;
                 }
             }
             s.l_any[li] = any;
             s.l_k[li] = (uint16_t)min(k, 0xffffu);
         }
+        mbar_wait(&s.bar, bar_parity);  // the right block has landed
+        bar_parity ^= 1u;
+        for (uint32_t sl = 0; sl < min(p.any_depth, SR); ++sl) {
+            const ulonglong2 ht = s.r_ht[sl][tid];
+            rany_h |= ht.x; rany_t |= ht.y;
+        }
+        if (!r_valid) rany_h = rany_t = 0;
+        // threshold <= 0 keeps every pair; an item without levels must reach stage C, which
+        // tells "both empty: score 0" from "one empty: IndexError upstream"
+        if (r_valid && (pass_all || kr == 0)) rany_h = rany_t = ~0ull;
         __syncthreads();
 
         // The funnel as one loop, so that each stage's code exists once: fill queue A from stage
@@ -284,7 +291,7 @@ jaccard_allpairs_kernel(const JaccardParams p) {
             auto bound_step = [&](uint32_t t, uint32_t li, uint32_t rc, uint32_t kmax, float ub) {
                 // steps beyond kmax read a repeated level and get weight 0
                 const uint32_t sr = min(t, SR) - 1;
-                const size_t at = (size_t)(min(t, SL) - 1) * p.L.n_items + l0 + li;
+                const size_t at = (size_t)(min(t, SL) - 1) * p.L.slot_stride + l0 + li;
                 const uint32_t ia = __ldg(p.L.slot_info + at), ib = s.r_info[sr][rc];
                 const uint32_t ih = bound_intersection(__ldg(l_slot_ht + at), ia, s.r_ht[sr][rc], ib,
                                                        exact_bits);

@@ -28,7 +28,7 @@ class NsmSets(C.Structure):
         "item_level_off", "level_tok_off", "tok", "level_head", "level_tail", "level_tail2",
         "level_info", "item_any", "item_k", "slot_ht", "slot_info")] + [
         ("n_items", C.c_uint32), ("n_levels", C.c_uint32), ("max_levels", C.c_uint32),
-        ("n_slots", C.c_uint32), ("exact_bits", C.c_uint32), ("reserved_", C.c_uint32)]
+        ("n_slots", C.c_uint32), ("exact_bits", C.c_uint32), ("slot_stride", C.c_uint32)]
 
 
 class NsmStrings(C.Structure):

@@ -15,10 +15,12 @@ Jaccard operands (``PackedSets``) — one cohort side, CSR over items -> levels 
     item_any        uint64[n_items, 2]  OR of (head, tail) over the levels compare_terms can use
                                         (levels 1..K-1, or level 0 when K == 1)
     item_k          uint32[n_items]     number of levels K of the item
-    slot_ht         uint64[n_slots, n_items, 2]  (head, tail) again, laid out by compare_terms step:
-    slot_info       uint32[n_slots, n_items]     slot t-1 holds level min(t, K-1) of each item
+    slot_ht         uint64[n_slots, stride, 2]   (head, tail) again, laid out by compare_terms step:
+    slot_info       uint32[n_slots, stride]      slot t-1 holds level min(t, K-1) of each item
                                         (n_slots = clamp(max K - 1, 1, 10); slot-major, so a block of
-                                        consecutive items is contiguous per step)
+                                        consecutive items is contiguous per step; stride = n_items
+                                        rounded up to 128 and zero-filled, so that every block of
+                                        128 items is one aligned, full-size bulk copy per step)
 
 Token ids are assigned in order of falling frequency over all packed sides, so ids 0..63 (the
 "head") are the 64 most frequent tokens: under the Zipf-like token statistics of questionnaire
@@ -95,6 +97,10 @@ class PackedSets:
     def n_slots(self) -> int:
         return self.slot_ht.shape[0]
 
+    @property
+    def slot_stride(self) -> int:
+        return self.slot_ht.shape[1]
+
     def level_sizes(self) -> np.ndarray:
         return np.diff(self.level_tok_off.astype(np.int64))
 
@@ -114,8 +120,8 @@ class PackedSets:
             self.tok[t0:t1].copy(), self.level_head[g0:g1].copy(), self.level_tail[g0:g1].copy(),
             self.level_tail2[g0:g1].copy(), self.level_info[g0:g1].copy(),
             self.item_any[begin:end].copy(), self.item_k[begin:end].copy(),
-            np.ascontiguousarray(self.slot_ht[:, begin:end]),
-            np.ascontiguousarray(self.slot_info[:, begin:end]), self.n_vocab,
+            _pad_slots(self.slot_ht[:, begin:end]), _pad_slots(self.slot_info[:, begin:end]),
+            self.n_vocab,
             self.exact_bits, self.max_levels)
 
 
@@ -172,6 +178,15 @@ class PackedStrings:
             self.max_len, None if self.perm is None else self.perm[begin:end].copy(), cls)
 
 
+def _pad_slots(a: np.ndarray) -> np.ndarray:
+    """Slot rows cut to a sub-range of items, re-padded to the 128-item stride."""
+    n = a.shape[1]
+    stride = max(128, (n + 127) // 128 * 128)
+    out = np.zeros((a.shape[0], stride) + a.shape[2:], dtype=a.dtype)
+    out[:, :n] = a
+    return out
+
+
 def _pad8(n):
     return (n + 7) // 8 * 8
 
@@ -184,6 +199,7 @@ WORD_CLASSES = 8   # 64-bit words per pattern the kernel instantiates: up to 512
 # ------------------------------------------------------------------------------------------
 HEAD_IDS = 64
 SLOT_CAP = 10
+SLOT_BLOCK = 128   # items per right block of the kernel
 SIG2_HASH_MULT = np.uint32(0x85EBCA77)
 
 
@@ -244,16 +260,17 @@ def finish_sets(item_level_off, level_tok_off, tok, n_vocab: int) -> PackedSets:
     # compare_terms' schedule, materialised: slot t-1 = level min(t, K-1)
     max_k = int(k.max()) if n_items else 0
     n_slots = min(max(max_k - 1, 1), SLOT_CAP)
-    slot_ht = np.zeros((n_slots, n_items, 2), dtype=np.uint64)
-    slot_info = np.zeros((n_slots, n_items), dtype=np.uint32)
+    stride = max(SLOT_BLOCK, (n_items + SLOT_BLOCK - 1) // SLOT_BLOCK * SLOT_BLOCK)
+    slot_ht = np.zeros((n_slots, stride, 2), dtype=np.uint64)
+    slot_info = np.zeros((n_slots, stride), dtype=np.uint32)
     has = k > 0
     if n_levels and has.any():
         base = item_level_off[:-1].astype(np.int64)
         for t in range(1, n_slots + 1):
             g = (base + np.minimum(t, np.maximum(k - 1, 0)))[has]
-            slot_ht[t - 1, has, 0] = head[g]
-            slot_ht[t - 1, has, 1] = tail[g]
-            slot_info[t - 1, has] = info[g]
+            slot_ht[t - 1, :n_items][has, 0] = head[g]
+            slot_ht[t - 1, :n_items][has, 1] = tail[g]
+            slot_info[t - 1, :n_items][has] = info[g]
     return PackedSets(item_level_off, level_tok_off, tok, head, tail, tail2, info, item_any,
                       np.minimum(k, 0xFFFFFFFF).astype(np.uint32), slot_ht, slot_info,
                       int(n_vocab), bool(exact_bits), max_k)
