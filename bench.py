@@ -58,6 +58,11 @@ WORKLOADS = {
     "term20k": dict(kind="term", n=20_000, n_right=20_000, thr=0.5, desc="reduced term (debug)"),
     "fuzzy20k": dict(kind="fuzzy", n=20_000, thr=0.7,
                      desc="fuzzy_match flat strings 20k x 20k, avg 60 chars, thr 0.7"),
+    "fuzzy200k": dict(kind="fuzzy", n=200_000, thr=0.7,
+                      desc="cfg3: fuzzy_match flat strings 200k x 200k, avg 60 chars, thr 0.7"),
+    "fuzzyterm10k": dict(kind="fuzzyterm", n=10_000, thr=0.5,
+                         desc="the reference's shipped config: fuzzy_match on Term (K 2-4 levels), "
+                              "10k x 10k items, cache_threshold 0.5"),
 }
 
 
@@ -104,7 +109,35 @@ def build_fuzzy(n: int, rank: int):
     return {"left": pl, "right": pr}, {"left": sl, "right": sr}, [("left", "right")]
 
 
+def build_fuzzyterm(n: int, rank: int):
+    """Term items as strings: per level the joined, processed token string QRatio sees."""
+    from napkon_string_matching import synthetic as syn
+    from napkon_string_matching.gpu import pack
+
+    vocab = syn.vocabulary()
+    raw, levels = {}, {}
+    for name, seed in (("left", syn.SEED_LEFT), ("right", syn.SEED_RIGHT)):
+        part_lens, flat = syn.term_level_sets(n, seed + 1000 * rank)
+        raw[name] = (part_lens, flat)
+        starts = np.concatenate([[0], np.cumsum(part_lens.sum(axis=1))])
+        items = []
+        for i in range(n):
+            pos, parts = int(starts[i]), []
+            for q in part_lens[i]:
+                if q:
+                    parts.append([vocab[int(v)] for v in flat[pos:pos + q]])
+                    pos += int(q)
+            items.append([sorted({w for part in parts[-j:] for w in part}, key=lambda w: (w.casefold(), w))
+                          for j in range(1, len(parts) + 1)])
+        levels[name] = items
+    pl, pr = pack.pack_strings(pack.fuzzy_level_strings(levels["left"]),
+                               pack.fuzzy_level_strings(levels["right"]))
+    return {"left": pl, "right": pr}, levels, [("left", "right")]
+
+
 def build_workload(wl: dict, rank: int):
+    if wl["kind"] == "fuzzyterm":
+        return build_fuzzyterm(wl["n"], rank)
     if wl["kind"] == "tokenids":
         return build_tokenids(wl["n"], rank)
     if wl["kind"] == "term":
@@ -124,6 +157,23 @@ def schedule_counts(left, right):
     hist_l = np.bincount(kl, minlength=kmax + 1).astype(np.float64)
     ks = np.arange(kmax + 1)
     evals = float((np.maximum.outer(ks, ks) * np.outer(hist_l, hist_r))[1:, 1:].sum())
+    if not hasattr(left, "tok") and kmax > 1:
+        # levelled strings: 8 * ceil(min/64) * max per evaluation, estimated from a 512 x 512 sample
+        # of items along compare_terms' schedule
+        rng = np.random.default_rng(0)
+        li = rng.integers(0, left.n_items, size=min(512, left.n_items))
+        ri = rng.integers(0, right.n_items, size=min(512, right.n_items))
+        ll, lr = left.level_lengths(), right.level_lengths()
+        lo, ro = left.item_level_off.astype(np.int64), right.item_level_off.astype(np.int64)
+        ops = n_ev = 0.0
+        for t in range(1, kmax + 1):
+            a = ll[lo[li] + np.minimum(t, kl[li] - 1)].astype(np.float64)
+            b = lr[ro[ri] + np.minimum(t, kr[ri] - 1)].astype(np.float64)
+            active = t <= np.maximum.outer(kl[li], kr[ri])
+            mn, mx = np.minimum.outer(a, b), np.maximum.outer(a, b)
+            ops += float((8.0 * np.ceil(mn / 64.0) * mx * active).sum())
+            n_ev += float(active.sum())
+        return evals, ops / max(n_ev, 1.0) * evals
     if not hasattr(left, "tok"):
         # flat strings: one evaluation per pair
         ll, lr = left.level_lengths().astype(np.float64), right.level_lengths().astype(np.float64)
@@ -248,7 +298,7 @@ def cpu_reference(workload: dict, raw, pairs, seconds: float, procs: int, packs=
     import multiprocessing as mp
 
     a, b = pairs[0]
-    if workload["kind"] == "fuzzy":
+    if workload["kind"] in ("fuzzy", "fuzzyterm"):
         from oracle import c_oracle
 
         os.environ["OMP_NUM_THREADS"] = str(procs)
@@ -259,8 +309,8 @@ def cpu_reference(workload: dict, raw, pairs, seconds: float, procs: int, packs=
         while time.perf_counter() - t_start < seconds:
             i = n_blocks % avail
             blk = left.rows(i * rows_per_block, min(left.n_items, (i + 1) * rows_per_block))
-            c_oracle.all_pairs(blk, right, workload["thr"], flat=True)
-            done_pairs += blk.n_items * right.n_items
+            c_oracle.all_pairs(blk, right, workload["thr"], flat=workload["kind"] == "fuzzy")
+            done_pairs += int(np.maximum.outer(blk.levels_per_item(), right.levels_per_item()).sum())
             n_blocks += 1
         wall = time.perf_counter() - t_start
         sample = (f"{n_blocks} blocks of {rows_per_block} x {right.n_items} strings of {a} x {b} "
@@ -312,7 +362,7 @@ def run_reference_arm(args, rank: int):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "int32+f64" if wl["kind"] != "fuzzy" else "u64+f64", "data": "synthetic",
+        "dtype": "int32+f64" if not wl["kind"].startswith("fuzzy") else "u64+f64", "data": "synthetic",
         "config": {"workload": args.workload, "desc": wl["desc"]},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
                          "sample": sample},
@@ -439,7 +489,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int32+f64" if wl["kind"] != "fuzzy" else "u64+f64", "data": "synthetic",
+            "dtype": "int32+f64" if not wl["kind"].startswith("fuzzy") else "u64+f64", "data": "synthetic",
             "config": {"workload": args.workload, "desc": wl["desc"],
                        "item_pairs_per_step_per_gpu": item_pairs_step,
                        "pair_scores_per_step_per_gpu": evals_step,

@@ -247,3 +247,51 @@ def test_jaccard_full_size_properties(engine):
     kept = (pos < len(key)) & (key[np.minimum(pos, len(key) - 1)] == probe)
     got, _ = c_oracle.score_pairs(pl, pr, li, ri)
     assert np.array_equal(got >= thr, kept)
+
+
+def _random_side(rng, n, vocab, max_k, max_size):
+    items = []
+    for _ in range(n):
+        k = int(rng.integers(0, max_k + 1))
+        items.append([[f"w{int(x)}" for x in rng.zipf(1.4, size=int(rng.integers(0, max_size + 1))) % vocab]
+                      for _ in range(k)])
+    return items
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_jaccard_random_ragged_inputs_vs_oracle(engine, seed):
+    """Ragged level counts (0 .. 14: beyond the 10 staged slots), empty levels, empty items,
+    vocabularies below and above the exact-bit limit; results AND exception flags must match."""
+    rng = np.random.default_rng(1000 + seed)
+    vocab = [30, 100, 129, 4000, 4000, 60000][seed]
+    L = _random_side(rng, int(rng.integers(1, 300)), vocab, [3, 14, 6, 14, 2, 5][seed], [6, 12, 40, 8, 3, 30][seed])
+    R = _random_side(rng, int(rng.integers(1, 400)), vocab, [3, 14, 6, 12, 2, 5][seed], [6, 12, 40, 8, 3, 30][seed])
+    pl, pr = pack.pack_sets(L, R)
+    for thr in (0.0, 0.08, 0.3, 0.55):
+        got, info = run_gpu(engine, pl, pr, thr)
+        want, oflags = c_oracle.all_pairs(pl, pr, thr)
+        assert_same_triples((got["left"], got["right"], got["score"]),
+                            (want["left"], want["right"], want["score"]))
+        if thr == 0.0:  # every pair reaches exact scoring: flags are complete
+            assert bool(info["flags"] & nsmlib.FLAG_ZERO_UNION) == bool(oflags & c_oracle.FLAG_ZERO_UNION)
+            assert bool(info["flags"] & nsmlib.FLAG_EMPTY_ITEM) == bool(oflags & c_oracle.FLAG_INDEX_ERROR)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_fuzzy_random_ragged_inputs_vs_oracle(engine, seed):
+    rng = np.random.default_rng(2000 + seed)
+    alpha = list("abcdefghijklmnopqrstuvwxyzäöüß0123456789 ")[: [8, 20, 41, 41][seed]]
+    max_len = [40, 90, 200, 500][seed]
+
+    def side(n, max_k):
+        return [["".join(rng.choice(alpha, size=int(rng.integers(0, max_len + 1)))).strip()
+                 for _ in range(int(rng.integers(0, max_k + 1)))] for _ in range(n)]
+
+    L, R = side(int(rng.integers(1, 120)), [1, 4, 3, 2][seed]), side(int(rng.integers(1, 150)), [1, 4, 2, 3][seed])
+    pl, pr = pack.pack_strings(L, R)
+    for thr in (0.0, 0.35, 0.6):
+        got, info = run_gpu(engine, pl, pr, thr)
+        want, oflags = c_oracle.all_pairs(pl, pr, thr)
+        assert_same_triples((got["left"], got["right"], got["score"]),
+                            (want["left"], want["right"], want["score"]))
+        assert bool(info["flags"] & nsmlib.FLAG_EMPTY_ITEM) == bool(oflags & c_oracle.FLAG_INDEX_ERROR)
