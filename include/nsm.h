@@ -62,6 +62,7 @@ typedef struct nsm_sets {
     const uint32_t *item_level_off; /* [n_items + 1] */
     const uint32_t *level_tok_off;  /* [n_levels + 1] */
     const uint32_t *tok;            /* [level_tok_off[n_levels]] ids ranked by falling frequency */
+    const uint8_t *tok_entry;       /* [same] first level of the item that holds the id (see nested) */
     const uint64_t *level_head;     /* [n_levels] exact bitset of the level's ids 0..63 */
     const uint64_t *level_tail;     /* [n_levels] signature of its ids >= 64 (exact iff exact_bits) */
     const uint64_t *level_tail2;    /* [n_levels] second, independent signature of the ids >= 64 */
@@ -76,6 +77,10 @@ typedef struct nsm_sets {
     uint32_t n_slots;    /* clamp(max_levels - 1, 1, 10) */
     uint32_t exact_bits; /* 1: vocabulary <= 128 ids, tail bit == id - 64, no token merge needed */
     uint32_t slot_stride; /* items per slot row: n_items rounded up to 128, zero-filled */
+    uint32_t nested;      /* 1: in every item level j is a subset of level j+1 (what gen_comp_value
+                             produces), so one intersection of the deepest levels with tok_entry
+                             yields the intersections of all level pairs */
+    uint32_t reserved_;
 } nsm_sets_t;
 
 /* One cohort side for fuzzy_match: per level the processed string QRatio sees

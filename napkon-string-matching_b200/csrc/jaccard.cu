@@ -26,8 +26,9 @@
 //              Six steps, straight-line, in two halves (steps 1..D, then the rest for the pairs
 //              whose bound can still reach the threshold); later steps' weight is granted in full.
 //   C  EXACT   per used level the exact |A & B| (popcount; only if both tail signatures collide,
-//              a warp-cooperative intersection of the tail ids), the reference's int/int float64
-//              division and its accumulation order; score >= threshold in float64.
+//              a warp-cooperative intersection of the tail ids - one per pair, of the deepest
+//              levels, when the levels are nested), the reference's int/int float64 division
+//              and its accumulation order; score >= threshold in float64.
 // Kept pairs go to a per-warp staging buffer and are flushed with one global atomic per ~50
 // records as coalesced 16-byte stores.
 #include "nsm_common.cuh"
@@ -115,6 +116,52 @@ __device__ __forceinline__ uint32_t warp_intersect_count(const uint32_t *__restr
     return c;
 }
 
+// Nested levels: one intersection of the two DEEPEST tail id lists gives the tail intersection of
+// every step.  An id held from level ea on the left and eb on the right is shared from step
+// max(1, ea, eb) on (step t uses level min(t, K-1) >= the entry level exactly when t >= it).
+// Returns, packed 8 bits per step (t = 1..16), the number of shared tail ids at each step;
+// all arguments warp-uniform, at most 255 shared ids (the caller checks min(na, nb) <= 255).
+__device__ __forceinline__ ulonglong2 warp_intersect_steps(const uint32_t *__restrict__ a,
+                                                           const uint8_t *__restrict__ ea, uint32_t na,
+                                                           const uint32_t *__restrict__ b,
+                                                           const uint8_t *__restrict__ eb, uint32_t nb,
+                                                           uint32_t kmax) {
+    ulonglong2 cnt = make_ulonglong2(0, 0);
+    if (na == 0 || nb == 0) return cnt;
+    if (na < nb) {
+        const uint32_t *tp = a; a = b; b = tp;
+        const uint8_t *te = ea; ea = eb; eb = te;
+        const uint32_t tn = na; na = nb; nb = tn;
+    }
+    const unsigned lane = lane_id();
+    for (uint32_t base = 0; base < na; base += 32) {
+        const bool valid = base + lane < na;
+        const uint32_t x = valid ? __ldg(a + base + lane) : 0u;
+        const uint32_t ex = valid ? (uint32_t)__ldg(ea + base + lane) : 0u;
+        uint32_t d = 0xffffu;  // first step at which my id is shared; 0xffff: never
+        if (nb <= 32) {
+            const uint32_t yb = lane < nb ? __ldg(b + lane) : 0xffffffffu;
+            const uint32_t ey = lane < nb ? (uint32_t)__ldg(eb + lane) : 0u;
+            for (uint32_t j = 0; j < nb; ++j) {
+                const uint32_t y = __shfl_sync(FULL_MASK, yb, j), e = __shfl_sync(FULL_MASK, ey, j);
+                if (valid && x == y) d = max(max(ex, e), 1u);
+            }
+        } else if (valid) {
+            uint32_t lo = 0, hi = nb;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (__ldg(b + mid) < x) lo = mid + 1; else hi = mid;
+            }
+            if (lo < nb && __ldg(b + lo) == x) d = max(max(ex, (uint32_t)__ldg(eb + lo)), 1u);
+        }
+        for (uint32_t t = 1; t <= kmax; ++t) {
+            const unsigned long long c = __popc(__ballot_sync(FULL_MASK, d <= t));
+            if (t <= 8) cnt.x += c << (8 * (t - 1)); else cnt.y += c << (8 * (t - 9));
+        }
+    }
+    return cnt;
+}
+
 // Upper bound of |A & B| of one level pair from the summaries; exact when the tails share no
 // bit.  Shared tail bits + the ids either side folded onto an occupied bit bound the shared tail
 // ids (a fold count of 255 is saturated: fall back to min(|A|, |B|)).  Branch-free.
@@ -138,6 +185,7 @@ jaccard_allpairs_kernel(const JaccardParams p) {
     unsigned long long *count = reinterpret_cast<unsigned long long *>(p.job.out_count);
     const bool flat = p.job.flat != 0;
     const bool exact_bits = p.L.exact_bits != 0 && p.R.exact_bits != 0;
+    const bool nested_mode = !exact_bits && p.L.nested != 0 && p.R.nested != 0;
     const double thr = p.job.threshold;
     const bool pass_all = !(p.thr_lo > -INFINITY) && !(p.thr_lo != p.thr_lo);  // thr <= 0
     const uint32_t SL = p.L.n_slots, SR = p.R.n_slots;
@@ -385,6 +433,43 @@ jaccard_allpairs_kernel(const JaccardParams p) {
                 const uint32_t kmax_warp = __reduce_max_sync(FULL_MASK, kmax);
                 double score = 0.0, w = flat ? 2.0 : 1.0;
                 uint32_t pjl = 0xffffffffu, pjr = 0xffffffffu, inter = 0, uni = 1, a = 0, b = 0;
+                // Nested levels (what gen_comp_value produces): the tail intersections of all steps
+                // come from ONE cooperative intersection of the deepest levels' tail ids.
+                bool nest_ok = nested_mode && kmax != 0 && kmax <= 16;
+                ulonglong2 tail_steps = make_ulonglong2(0, 0);
+                if (nested_mode) {  // kernel-uniform
+                    bool need_deep = false;
+                    uint32_t off_a = 0, off_b = 0, n_a = 0, n_b = 0;
+                    if (nest_ok) {
+                        uint32_t ia, ib;
+                        const ulonglong2 A = left_level(c_l, kmax, kl, ia);
+                        const ulonglong2 B = right_level(rc, c_r, kmax, c_kr, ib);
+                        if (A.y & B.y) {
+                            const uint32_t hl = __popcll(A.x), hr = __popcll(B.x);
+                            n_a = (ia & 0xffffu) - hl; n_b = (ib & 0xffffu) - hr;
+                            if (min(n_a, n_b) > 255u) {
+                                nest_ok = false;  // counts would not fit: per-level path below
+                            } else {
+                                const uint32_t gl = lg0 + kl - 1, gr = rg0 + c_kr - 1;
+                                const uint64_t t2l = __ldg(p.L.level_tail2 + gl), t2r = __ldg(p.R.level_tail2 + gr);
+                                off_a = __ldg(p.L.level_tok_off + gl) + hl;
+                                off_b = __ldg(p.R.level_tok_off + gr) + hr;
+                                need_deep = (t2l & t2r) != 0;
+                            }
+                        }
+                    }
+                    unsigned todo = __ballot_sync(FULL_MASK, need_deep);
+                    while (todo) {
+                        const int src = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const uint32_t oa = __shfl_sync(FULL_MASK, off_a, src), ob = __shfl_sync(FULL_MASK, off_b, src);
+                        const ulonglong2 c = warp_intersect_steps(
+                            p.L.tok + oa, p.L.tok_entry + oa, __shfl_sync(FULL_MASK, n_a, src),
+                            p.R.tok + ob, p.R.tok_entry + ob, __shfl_sync(FULL_MASK, n_b, src),
+                            __shfl_sync(FULL_MASK, kmax, src));
+                        if ((int)lane == src) { tail_steps = c; ++st_merges; }
+                    }
+                }
                 // the left summaries come through L2: keep the loads of the next two steps in
                 // flight while the current step is scored
                 const uint32_t kl1 = max(kl, 1u);
@@ -413,6 +498,9 @@ jaccard_allpairs_kernel(const JaccardParams p) {
                             if (tb) {
                                 if (exact_bits) {
                                     inter += __popcll(tb);
+                                } else if (nest_ok) {
+                                    inter += (uint32_t)((t <= 8 ? tail_steps.x >> (8 * (t - 1))
+                                                                : tail_steps.y >> (8 * (t - 9))) & 0xffu);
                                 } else {  // ids are sorted: the tail ids follow the head ids
                                     need = true; hl = __popcll(A.x); hr = __popcll(B.x);
                                 }

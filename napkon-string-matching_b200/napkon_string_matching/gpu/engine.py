@@ -103,7 +103,8 @@ class Engine:
         tensors = [self._to_device(a) for a in (pinned if pinned is not None else arrays)]
         if isinstance(packed, PackedSets):
             st = nsmlib.NsmSets(*[t.data_ptr() for t in tensors], packed.n_items, packed.n_levels,
-                                packed.max_levels, packed.n_slots, int(packed.exact_bits), packed.slot_stride)
+                                packed.max_levels, packed.n_slots, int(packed.exact_bits), packed.slot_stride,
+                                int(packed.nested), 0)
             per_level = packed.level_sizes()
             kind = "sets"
         else:

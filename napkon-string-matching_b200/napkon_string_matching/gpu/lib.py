@@ -25,10 +25,11 @@ EXPORTS = ("nsm_version", "nsm_last_error", "nsm_last_launch_count", "nsm_jaccar
 
 class NsmSets(C.Structure):
     _fields_ = [(name, C.c_void_p) for name in (
-        "item_level_off", "level_tok_off", "tok", "level_head", "level_tail", "level_tail2",
+        "item_level_off", "level_tok_off", "tok", "tok_entry", "level_head", "level_tail", "level_tail2",
         "level_info", "item_any", "item_k", "slot_ht", "slot_info")] + [
         ("n_items", C.c_uint32), ("n_levels", C.c_uint32), ("max_levels", C.c_uint32),
-        ("n_slots", C.c_uint32), ("exact_bits", C.c_uint32), ("slot_stride", C.c_uint32)]
+        ("n_slots", C.c_uint32), ("exact_bits", C.c_uint32), ("slot_stride", C.c_uint32),
+        ("nested", C.c_uint32), ("reserved_", C.c_uint32)]
 
 
 class NsmStrings(C.Structure):

@@ -7,6 +7,9 @@ Jaccard operands (``PackedSets``) — one cohort side, CSR over items -> levels 
     item_level_off  uint32[n_items+1]   levels of item i are item_level_off[i]:item_level_off[i+1]
     level_tok_off   uint32[n_levels+1]  tokens of level g are tok[level_tok_off[g]:level_tok_off[g+1]]
     tok             uint32[n_tok]       token ids, sorted and unique inside a level
+    tok_entry       uint8[n_tok]        first level of the item that holds this id (levels made by
+                                        gen_comp_value are nested: level j is a subset of level
+                                        j+1; ``nested`` says whether that holds for every item)
     level_head      uint64[n_levels]    exact bitset of the level's ids 0..63
     level_tail      uint64[n_levels]    signature of the ids >= 64 (bit = id - 64 if the whole
                                         vocabulary has <= 128 ids, else a multiplicative hash)
@@ -68,6 +71,7 @@ class PackedSets:
     item_level_off: np.ndarray
     level_tok_off: np.ndarray
     tok: np.ndarray
+    tok_entry: np.ndarray
     level_head: np.ndarray
     level_tail: np.ndarray
     level_tail2: np.ndarray
@@ -79,6 +83,7 @@ class PackedSets:
     n_vocab: int
     exact_bits: bool
     max_levels: int = 0
+    nested: bool = False
 
     @property
     def n_items(self) -> int:
@@ -89,7 +94,7 @@ class PackedSets:
         return len(self.level_tok_off) - 1
 
     def arrays(self):
-        return [self.item_level_off, self.level_tok_off, self.tok, self.level_head,
+        return [self.item_level_off, self.level_tok_off, self.tok, self.tok_entry, self.level_head,
                 self.level_tail, self.level_tail2, self.level_info, self.item_any, self.item_k,
                 self.slot_ht, self.slot_info]
 
@@ -117,12 +122,13 @@ class PackedSets:
         return PackedSets(
             (self.item_level_off[begin : end + 1] - np.uint32(g0)).astype(np.uint32),
             (self.level_tok_off[g0 : g1 + 1] - np.uint32(t0)).astype(np.uint32),
-            self.tok[t0:t1].copy(), self.level_head[g0:g1].copy(), self.level_tail[g0:g1].copy(),
+            self.tok[t0:t1].copy(), self.tok_entry[t0:t1].copy(), self.level_head[g0:g1].copy(),
+            self.level_tail[g0:g1].copy(),
             self.level_tail2[g0:g1].copy(), self.level_info[g0:g1].copy(),
             self.item_any[begin:end].copy(), self.item_k[begin:end].copy(),
             _pad_slots(self.slot_ht[:, begin:end]), _pad_slots(self.slot_info[:, begin:end]),
             self.n_vocab,
-            self.exact_bits, self.max_levels)
+            self.exact_bits, self.max_levels, self.nested)
 
 
 @dataclass
@@ -271,9 +277,36 @@ def finish_sets(item_level_off, level_tok_off, tok, n_vocab: int) -> PackedSets:
             slot_ht[t - 1, :n_items][has, 0] = head[g]
             slot_ht[t - 1, :n_items][has, 1] = tail[g]
             slot_info[t - 1, :n_items][has] = info[g]
-    return PackedSets(item_level_off, level_tok_off, tok, head, tail, tail2, info, item_any,
-                      np.minimum(k, 0xFFFFFFFF).astype(np.uint32), slot_ht, slot_info,
-                      int(n_vocab), bool(exact_bits), max_k)
+    tok_entry, nested = _entry_levels(item_level_off, level_tok_off, tok, k)
+    return PackedSets(item_level_off, level_tok_off, tok, tok_entry, head, tail, tail2, info,
+                      item_any, np.minimum(k, 0xFFFFFFFF).astype(np.uint32), slot_ht, slot_info,
+                      int(n_vocab), bool(exact_bits), max_k, nested)
+
+
+def _entry_levels(item_level_off, level_tok_off, tok, k) -> Tuple[np.ndarray, bool]:
+    """Per token row the first level of its item that holds the id, and whether every item's
+    levels are nested (each id is held by all levels from its entry level to the deepest)."""
+    n_levels, n_tok = len(level_tok_off) - 1, len(tok)
+    if n_tok == 0:
+        return np.zeros(0, dtype=np.uint8), True
+    sizes = np.diff(level_tok_off.astype(np.int64))
+    level_item = np.repeat(np.arange(len(k), dtype=np.int64), k)
+    level_j = np.arange(n_levels, dtype=np.int64) - item_level_off[:-1].astype(np.int64)[level_item]
+    row_item = np.repeat(level_item, sizes)
+    row_j = np.repeat(level_j, sizes)
+    key = row_item * (int(tok.max()) + 1) + tok.astype(np.int64)      # (item, id)
+    order = np.lexsort((row_j, key))
+    skey, sj = key[order], row_j[order]
+    first = np.ones(n_tok, dtype=bool)
+    first[1:] = skey[1:] != skey[:-1]
+    group = np.cumsum(first) - 1
+    entry_of_group = sj[first]
+    count_of_group = np.bincount(group)
+    k_of_group = k[row_item[order][first]]
+    nested = bool(np.all(count_of_group == k_of_group - entry_of_group)) and int(k.max(initial=0)) <= 255
+    entry = np.empty(n_tok, dtype=np.int64)
+    entry[order] = entry_of_group[group]
+    return np.minimum(entry, 255).astype(np.uint8), nested
 
 
 def rank_by_frequency(codes_per_side: List[np.ndarray], n_vocab: int) -> List[np.ndarray]:

@@ -32,7 +32,7 @@ def test_library_loads_and_exports_every_declared_symbol():
 def test_struct_layouts_match_the_header():
     from napkon_string_matching.gpu import lib as nsmlib
 
-    assert ctypes.sizeof(nsmlib.NsmSets) == 11 * 8 + 6 * 4
+    assert ctypes.sizeof(nsmlib.NsmSets) == 12 * 8 + 8 * 4
     assert ctypes.sizeof(nsmlib.NsmStrings) == 4 * 8 + 6 * 4 + 8 * 4
     assert nsmlib.NsmJob.threshold.offset == 16
     assert nsmlib.NsmJob.out_pairs.offset == 40

@@ -295,3 +295,32 @@ def test_fuzzy_random_ragged_inputs_vs_oracle(engine, seed):
         assert_same_triples((got["left"], got["right"], got["score"]),
                             (want["left"], want["right"], want["score"]))
         assert bool(info["flags"] & nsmlib.FLAG_EMPTY_ITEM) == bool(oflags & c_oracle.FLAG_INDEX_ERROR)
+
+
+def test_jaccard_nested_levels_single_intersection_and_its_fallbacks(engine):
+    """gen_comp_value's levels are nested, which the kernel uses to intersect the tail ids once
+    per pair.  Cover the cases where it must fall back to per-level intersections: more than 16
+    steps, more than 255 tail ids, or one side not nested."""
+    rng = np.random.default_rng(77)
+
+    def suffix_items(n, max_k, per_part, vocab):
+        out = []
+        for _ in range(n):
+            parts = [[f"w{int(x)}" for x in rng.zipf(1.3, size=int(rng.integers(1, per_part + 1))) % vocab]
+                     for _ in range(int(rng.integers(1, max_k + 1)))]
+            out.append([sorted({w for part in parts[-j:] for w in part}) for j in range(1, len(parts) + 1)])
+        return out
+
+    for max_k, per_part, vocab in ((6, 4, 3000), (22, 2, 3000), (3, 420, 9000)):
+        L, R = suffix_items(150, max_k, per_part, vocab), suffix_items(170, max_k, per_part, vocab)
+        pl, pr = pack.pack_sets(L, R)
+        assert pl.nested and pr.nested and not pl.exact_bits
+        for thr in (0.0, 0.2):
+            _, info = check_against_oracle(engine, pl, pr, thr)
+        assert info["stats"]["level_merges"] > 0
+    # one side not nested: per-level path
+    L = suffix_items(100, 5, 4, 3000)
+    R = [[[f"w{int(x)}" for x in rng.integers(0, 3000, size=5)] for _ in range(3)] for _ in range(120)]
+    pl, pr = pack.pack_sets(L, R)
+    assert pl.nested and not pr.nested
+    check_against_oracle(engine, pl, pr, 0.0)
