@@ -56,6 +56,9 @@ WORKLOADS = {
     "defs1m": dict(kind="term", n=1_000_000, n_right=20_000, thr=0.5, defs=True,
                    desc="cfg4: 1M cohort items x 20k GECCO/KDS-style definitions, Tokens Jaccard, thr 0.5"),
     "term20k": dict(kind="term", n=20_000, n_right=20_000, thr=0.5, desc="reduced term (debug)"),
+    "variable20k": dict(kind="variable", n=20_000, thr=0.9,
+                        desc="the `variables` step: 20k x 20k items compared on the Variable column "
+                             "(a str: one level per character suffix, K = 12-16), thr 0.9"),
     "fuzzy20k": dict(kind="fuzzy", n=20_000, thr=0.7,
                      desc="fuzzy_match flat strings 20k x 20k, avg 60 chars, thr 0.7"),
     "fuzzy200k": dict(kind="fuzzy", n=200_000, thr=0.7,
@@ -135,7 +138,24 @@ def build_fuzzyterm(n: int, rank: int):
     return {"left": pl, "right": pr}, levels, [("left", "right")]
 
 
+def build_variable(n: int, rank: int):
+    """Variable names as the reference compares them: gen_comp_value of a str (Q2)."""
+    from napkon_string_matching.gpu import pack
+    from napkon_string_matching.text.tokenize import gen_comp_value
+
+    levels = {}
+    for name, seed in (("left", 1), ("right", 2)):
+        rng = np.random.default_rng(seed + 1000 * rank)
+        names = [f"{'gec_' if rng.random() < 0.2 else ''}{name[0]}{int(rng.integers(0, 4))}_v{int(rng.integers(0, 3 * n)):07d}"
+                 for _ in range(n)]
+        levels[name] = [gen_comp_value(v) for v in names]
+    pl, pr = pack.pack_sets(levels["left"], levels["right"])
+    return {"left": pl, "right": pr}, levels, [("left", "right")]
+
+
 def build_workload(wl: dict, rank: int):
+    if wl["kind"] == "variable":
+        return build_variable(wl["n"], rank)
     if wl["kind"] == "fuzzyterm":
         return build_fuzzyterm(wl["n"], rank)
     if wl["kind"] == "tokenids":
@@ -320,11 +340,17 @@ def cpu_reference(workload: dict, raw, pairs, seconds: float, procs: int, packs=
 
     n_right, rows_per_block = 1000, 40
     func, thr = "intersection_vs_union", workload["thr"]
-    levels = _levels_from_ids if workload["kind"] == "tokenids" else _levels_from_parts
-    n_right = min(n_right, len(raw[b][0]))
-    right = levels(*raw[b], 0, n_right)
-    avail = max(1, len(raw[a][0]) // rows_per_block)
-    block = lambda i: levels(*raw[a], (i % avail) * rows_per_block, (i % avail + 1) * rows_per_block)
+    if workload["kind"] == "variable":   # raw holds the level lists themselves
+        n_right = min(n_right, len(raw[b]))
+        right = raw[b][:n_right]
+        avail = max(1, len(raw[a]) // rows_per_block)
+        block = lambda i: raw[a][(i % avail) * rows_per_block:(i % avail + 1) * rows_per_block]
+    else:
+        levels = _levels_from_ids if workload["kind"] == "tokenids" else _levels_from_parts
+        n_right = min(n_right, len(raw[b][0]))
+        right = levels(*raw[b], 0, n_right)
+        avail = max(1, len(raw[a][0]) // rows_per_block)
+        block = lambda i: levels(*raw[a], (i % avail) * rows_per_block, (i % avail + 1) * rows_per_block)
     done_evals = done_pairs = n_blocks = 0
     t_start = time.perf_counter()
     with mp.get_context("fork").Pool(procs) as pool:

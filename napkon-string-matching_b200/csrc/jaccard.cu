@@ -154,11 +154,17 @@ __device__ __forceinline__ ulonglong2 warp_intersect_steps(const uint32_t *__res
             }
             if (lo < nb && __ldg(b + lo) == x) d = max(max(ex, (uint32_t)__ldg(eb + lo)), 1u);
         }
-        for (uint32_t t = 1; t <= kmax; ++t) {
-            const unsigned long long c = __popc(__ballot_sync(FULL_MASK, d <= t));
-            if (t <= 8) cnt.x += c << (8 * (t - 1)); else cnt.y += c << (8 * (t - 9));
-        }
+        // my id counts for every step t >= d: a one in the bytes d-1 .. 15, summed over the warp
+        // (at most 32 per byte and chunk, at most 255 in total: bytes never carry into each other)
+        const uint64_t ones = 0x0101010101010101ull;
+        const uint64_t lo = d <= 8 ? ones << (8 * (d - 1)) : 0ull;
+        const uint64_t hi = d <= 8 ? ones : (d <= 16 ? ones << (8 * (d - 9)) : 0ull);
+        cnt.x += (uint64_t)__reduce_add_sync(FULL_MASK, (uint32_t)lo) |
+                 ((uint64_t)__reduce_add_sync(FULL_MASK, (uint32_t)(lo >> 32)) << 32);
+        cnt.y += (uint64_t)__reduce_add_sync(FULL_MASK, (uint32_t)hi) |
+                 ((uint64_t)__reduce_add_sync(FULL_MASK, (uint32_t)(hi >> 32)) << 32);
     }
+    (void)kmax;
     return cnt;
 }
 
