@@ -89,7 +89,9 @@ __device__ __forceinline__ uint32_t lcs_bitparallel(const uint64_t *__restrict__
             const uint64_t sum = S[x] + u;
             const uint64_t sum2 = sum + carry;
             if (W > 1) carry = (sum < u) | (sum2 < sum);
-            S[x] = sum2 | (S[x] - u);
+            // u is a subset of S, so S - u == S & ~M: one three-input logic op per half instead
+            // of a subtract with borrow
+            S[x] = sum2 | (S[x] & ~M);
         }
     };
     uint32_t j = 0;
