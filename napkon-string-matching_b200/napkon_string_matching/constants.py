@@ -1,4 +1,7 @@
-LOG_FORMAT = "%(asctime)s\t%(levelname)s\t%(name)s\t%(message)s"
+"""Names shared across the package: the three NAPKON cohorts and the log line layout
+(tab separated: time, level, logger, message)."""
 
-HAP, POP, SUEP = "hap", "pop", "suep"
-COHORTS = [HAP, POP, SUEP]
+COHORTS = ["hap", "pop", "suep"]
+HAP, POP, SUEP = COHORTS
+
+LOG_FORMAT = "\t".join("%({})s".format(field) for field in ("asctime", "levelname", "name", "message"))

@@ -14,6 +14,7 @@ from napkon_string_matching.types.comparable_data import ComparableColumns, Comp
 
 
 class Columns(Enum):
+    """Columns of a cohort's data set table besides the comparable ones."""
     SHEET = "Sheet"
     FILE = "File"
     HEADER = "Header"
@@ -26,20 +27,26 @@ class Columns(Enum):
 
 
 class Questionnaire(ComparableData):
-    __columns__ = list(ComparableColumns) + list(Columns)
+    """Items of one cohort questionnaire."""
+
+    __columns__ = [*ComparableColumns, *Columns]
     __category_column__ = Columns.CATEGORY.value
     __column_mapping__ = {Columns.PARAMETER.value: comp.Columns.PARAMETER.value}
 
     def concat(self, others: List["Questionnaire"]):
+        """A new questionnaire holding the rows of this one followed by the others'."""
         if not others:
             return self
-        if not isinstance(others[0], Questionnaire):
-            raise TypeError("'other' should be of type '{}' but is of type '{}'".format(
-                type(self).__name__, type(others[0]).__name__))
-        return self.__class__(pd.concat([self._data, *[o._data for o in others]], ignore_index=True))
+        wrong = next((o for o in others if not isinstance(o, Questionnaire)), None)
+        if wrong is not None:
+            raise TypeError(f"'other' should be of type '{type(self).__name__}' but is of type "
+                            f"'{type(wrong).__name__}'")
+        frames = [self._data] + [o._data for o in others]
+        return type(self)(pd.concat(frames, ignore_index=True))
 
     def add_terms(self, language: str = "german"):
-        self.term = [
-            self.gen_term(*(header or []), question, parameter)
-            for header, question, parameter in zip(self.header, self.question, self.parameter)
-        ]
+        """``Term = [*header parts, question, parameter]`` with empty parts dropped."""
+        terms = []
+        for header, question, parameter in zip(self.header, self.question, self.parameter):
+            terms.append(self.gen_term(*(header or ()), question, parameter))
+        self.term = terms

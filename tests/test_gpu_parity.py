@@ -324,3 +324,25 @@ def test_jaccard_nested_levels_single_intersection_and_its_fallbacks(engine):
     pl, pr = pack.pack_sets(L, R)
     assert pl.nested and not pr.nested
     check_against_oracle(engine, pl, pr, 0.0)
+
+
+def test_unsupported_inputs_raise_instead_of_falling_back(engine):
+    # a right-hand string longer than 512 characters: no kernel width for it
+    pl, pr = pack.pack_strings([["abc"]], [["x" * 600]])
+    with pytest.raises(nsmlib.NsmError, match="512|handles"):
+        engine.all_pairs(engine.upload(pl), engine.upload(pr), 0.1, flat=True)
+    # flat scoring needs one level per item
+    pl, pr = pack.pack_sets([[["a"], ["b"]]], [[["a"]]])
+    with pytest.raises(nsmlib.NsmError, match="one level"):
+        engine.all_pairs(engine.upload(pl), engine.upload(pr), 0.1, flat=True)
+    # sets against strings
+    ql, = pack.pack_strings([["abc"]])
+    with pytest.raises(TypeError):
+        engine.all_pairs(engine.upload(pl), engine.upload(ql), 0.1)
+    # maximum sizes that ARE supported: a 60000-token level, a 512-character string
+    big = [f"t{i}" for i in range(60000)]
+    pl, pr = pack.pack_sets([[big]], [[big[:30000] + ["zz"]], [["t5"]]])
+    out, _ = check_against_oracle(engine, pl, pr, 0.0, flat=True)
+    assert sorted(out["score"].tolist()) == [1 / 60000, 30000 / 60001]
+    pl, pr = pack.pack_strings([["ab" * 256]], [["ba" * 256], ["a" * 512]])
+    check_against_oracle(engine, pl, pr, 0.0, flat=True)

@@ -192,3 +192,12 @@ def test_pack_strings_alphabet_and_rows():
     sub = pl.rows(1, 2)
     assert sub.n_items == 1 and list(sub.level_lengths()) == [8] and list(sub.level_chr_off) == [0]
     assert "".join(alphabet[c] for c in sub.level_string_codes(0)) == "größe 12"
+
+
+def test_pack_limits_are_loud():
+    with pytest.raises(pack.PackError):       # more code points than one byte can name
+        pack.pack_strings([["".join(chr(0x4E00 + i) for i in range(300))]])
+    with pytest.raises(pack.PackError):       # a level beyond the 16-bit size field
+        pack.pack_sets([[[f"t{i}" for i in range(70000)]]])
+    (p,) = pack.pack_strings([["x" * 600], ["y"]])   # longer than the kernel's 8 words: last class
+    assert int(p.class_end[-1]) == 1 and p.n_items == 2
