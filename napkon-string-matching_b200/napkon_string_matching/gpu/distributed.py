@@ -7,7 +7,7 @@ records themselves are concatenated on the host through a gloo group.
 """
 from __future__ import annotations
 
-from typing import Callable, List, Optional, Tuple
+from typing import Callable, List, Tuple
 
 import numpy as np
 import torch

@@ -7,7 +7,7 @@ PyTorch is used for device memory, pinned host memory and streams only.  No GPU 
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
@@ -17,10 +17,6 @@ from napkon_string_matching.gpu import lib as nsmlib
 from napkon_string_matching.gpu.pack import PackedSets, PackedStrings
 
 PAIR_DTYPE = nsmlib.PAIR_DTYPE
-
-
-class ScoreError(Exception):
-    """Carries the reference's exception type for inputs its pair loop would have raised on."""
 
 
 def _require_cuda() -> None:

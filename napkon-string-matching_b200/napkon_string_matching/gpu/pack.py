@@ -49,7 +49,7 @@ with the narrowest bit-vectors; ``perm`` maps a stored position back to the call
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Iterable, List, Sequence, Tuple
 
 import numpy as np

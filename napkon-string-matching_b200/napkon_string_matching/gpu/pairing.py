@@ -10,7 +10,7 @@ comparable_data.py): category predicate :464-476, black-list exclusion :523-552,
 """
 from __future__ import annotations
 
-from typing import Callable, List, Optional, Sequence, Tuple
+from typing import Callable, List, Optional, Sequence
 
 import numpy as np
 import pandas as pd

@@ -17,12 +17,12 @@ from enum import Enum
 from pathlib import Path
 from typing import Dict, List, Tuple
 
-import numpy as np
 import pandas as pd
 
 import napkon_string_matching.compare.score_functions
 from napkon_string_matching.text import tokenize as _tok
-from napkon_string_matching.types.comparable import COLUMN_NAMES, QUESTION_OUTPUT, Columns, Comparable
+from napkon_string_matching.types.comparable import (COLUMN_NAMES, QUESTION_OUTPUT, Columns,  # noqa: F401
+                                                     Comparable)
 from napkon_string_matching.types.data import Data, gen_hash
 from napkon_string_matching.types.mapping import Mapping
 
