@@ -294,9 +294,17 @@ def _entry_levels(item_level_off, level_tok_off, tok, k) -> Tuple[np.ndarray, bo
     level_j = np.arange(n_levels, dtype=np.int64) - item_level_off[:-1].astype(np.int64)[level_item]
     row_item = np.repeat(level_item, sizes)
     row_j = np.repeat(level_j, sizes)
-    key = row_item * (int(tok.max()) + 1) + tok.astype(np.int64)      # (item, id)
-    order = np.lexsort((row_j, key))
-    skey, sj = key[order], row_j[order]
+    span, kspan = int(tok.max()) + 1, int(k.max()) + 1
+    # one sort of the combined (item, id, level) key; rows of one (item, id) end up adjacent with
+    # their levels ascending
+    if len(k) * span * kspan < 2 ** 62:
+        key = (row_item * span + tok.astype(np.int64)) * kspan + row_j
+        order = np.argsort(key, kind="stable")
+        skey = key[order] // kspan
+    else:  # the combined key would overflow 64 bits: three-key sort
+        order = np.lexsort((row_j, tok, row_item))
+        skey = np.cumsum(np.concatenate([[0], (np.diff(row_item[order]) != 0) | (np.diff(tok[order].astype(np.int64)) != 0)]))
+    sj = row_j[order]
     first = np.ones(n_tok, dtype=bool)
     first[1:] = skey[1:] != skey[:-1]
     group = np.cumsum(first) - 1
@@ -339,16 +347,26 @@ def _csr_from_nested(items_levels: Sequence[Sequence[Sequence]]) -> Tuple[np.nda
 
 
 def _sort_unique_levels(level_off: np.ndarray, codes: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
-    """Sort ids inside every level and drop duplicates (the score function works on sets)."""
+    """Sort ids inside every level and drop duplicates (the score function works on sets).
+    One sort of a combined (level, id) key instead of a two-key lexsort."""
     n_levels = len(level_off) - 1
     sizes = np.diff(level_off)
+    if len(codes) == 0:
+        return np.zeros(n_levels + 1, dtype=np.int64), codes.astype(np.int64)
+    span = int(codes.max()) + 1
     level_id = np.repeat(np.arange(n_levels, dtype=np.int64), sizes)
-    order = np.lexsort((codes, level_id))
-    codes, level_id = codes[order], level_id[order]
-    keep = np.ones(len(codes), dtype=bool)
-    if len(codes) > 1:
+    if n_levels * span < 2 ** 62:
+        key = np.sort(level_id * span + codes)
+        keep = np.ones(len(key), dtype=bool)
+        keep[1:] = key[1:] != key[:-1]
+        key = key[keep]
+        level_id, codes = key // span, key % span
+    else:  # cannot happen with 32-bit ids and < 2^30 levels; kept for safety
+        order = np.lexsort((codes, level_id))
+        codes, level_id = codes[order], level_id[order]
+        keep = np.ones(len(codes), dtype=bool)
         keep[1:] = (codes[1:] != codes[:-1]) | (level_id[1:] != level_id[:-1])
-    codes, level_id = codes[keep], level_id[keep]
+        codes, level_id = codes[keep], level_id[keep]
     new_sizes = np.bincount(level_id, minlength=n_levels).astype(np.int64)
     new_off = np.zeros(n_levels + 1, dtype=np.int64)
     np.cumsum(new_sizes, out=new_off[1:])
