@@ -141,6 +141,56 @@ int nsm_jaccard_allpairs(const nsm_sets_t *left, const nsm_sets_t *right, const 
 int nsm_qratio_allpairs(const nsm_strings_t *left, const nsm_strings_t *right, const nsm_job_t *job,
                         void *stream);
 
+/* ---- device-side token packing ---------------------------------------------
+ * Builds every array of nsm_sets_t on the GPU from the dictionary codes of the tokens, i.e. what
+ * ComparableData.gen_comp_value (comparable_data.py:283-285) yields after the host has tokenised
+ * the items and mapped token strings to integer codes (exact string identity, Q3).  The result is
+ * bit-identical to the host packer (napkon_string_matching/gpu/pack.py:finish_sets). */
+#define NSM_RAW_SUFFIX_PARTS 0 /* group g of an item is one part of its value; level j is the id set
+                                  of the item's last j+1 parts (items[-i:], comparable_data.py:284) */
+#define NSM_RAW_LEVELS 1       /* group g of an item is its level j, given explicitly */
+
+#define NSM_PACK_MAX_ITEM_IDS 1024u /* ids one item may hold over all its groups */
+
+/* bits of *flags written by the pack entry points */
+#define NSM_PACK_FLAG_TOO_LARGE 1u  /* an item holds more than NSM_PACK_MAX_ITEM_IDS ids */
+#define NSM_PACK_FLAG_NOT_NESTED 2u /* some level is not a subset of the next one (never with parts) */
+#define NSM_PACK_FLAG_BAD_ID 4u     /* an id >= n_vocab */
+
+typedef struct nsm_raw_sets {
+    const uint32_t *item_grp_off; /* [n_items + 1] groups (parts or levels) of item i */
+    const uint32_t *grp_id_off;   /* [n_groups + 1] ids of group g */
+    const uint32_t *ids;          /* [n_ids] dictionary codes < n_vocab, any order, duplicates allowed */
+    const uint32_t *rank;         /* [n_vocab] renumbering applied to every id (frequency rank), or NULL */
+    uint32_t n_items;
+    uint32_t n_groups;
+    uint32_t n_ids;
+    uint32_t n_vocab;
+    uint32_t mode; /* NSM_RAW_* */
+    uint32_t reserved_;
+} nsm_raw_sets_t;
+
+/* counts[id] += occurrences of id in raw->ids (raw->rank is ignored).  counts: device, [n_vocab],
+ * zeroed by the caller before the first side is counted. */
+int nsm_pack_count_ids(const nsm_raw_sets_t *raw, uint32_t *counts, void *stream);
+
+/* Bytes of device scratch nsm_pack_sets_measure needs for n_items items. */
+uint64_t nsm_pack_scratch_bytes(uint32_t n_items);
+
+/* Pass 1: item_tok_off[i] (device, [n_items + 1]) = number of token rows (sum of the level sizes
+ * after sort + unique) of all items before i; totals[0] = their total, totals[1] = NSM_PACK_FLAG_*
+ * (device uint64[2]).  The caller reads totals, allocates the nsm_sets_t arrays and calls fill. */
+int nsm_pack_sets_measure(const nsm_raw_sets_t *raw, uint32_t *item_tok_off, uint64_t *totals,
+                          void *scratch, uint64_t scratch_bytes, void *stream);
+
+/* Pass 2: fills every array `out` points to (device memory of the sizes nsm_sets_t documents, with
+ * n_levels == raw->n_groups, tok / tok_entry of totals[0] rows; written through the const
+ * pointers).  The caller sets out->n_items, n_levels, max_levels, n_slots, slot_stride and
+ * exact_bits; out->nested is not touched (it is !(flags & NSM_PACK_FLAG_NOT_NESTED) &&
+ * max_levels <= 255).  flags: device uint32, OR of NSM_PACK_FLAG_*. */
+int nsm_pack_sets_fill(const nsm_raw_sets_t *raw, const uint32_t *item_tok_off, const nsm_sets_t *out,
+                       uint32_t *flags, void *stream);
+
 /* Integer-pipe micro-benchmarks used as roofline denominators: every thread of
  * a blocks x threads grid runs `iters` rounds of 8 independent chains x 4 dependent ops of
  * `kind` (0: LOP3, 1: IADD3, 2: POPC, 3: 64-bit add/sub/and/or LCS step).  *ops_per_thread

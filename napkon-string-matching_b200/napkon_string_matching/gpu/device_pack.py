@@ -1,0 +1,219 @@
+"""
+Device-side token packing: the CUDA counterpart of ``pack.finish_sets`` and of
+the integer fast paths ``pack.pack_part_id_sets`` / ``pack.pack_suffix_id_sets``.
+
+The host keeps what north_star assigns to it — tokenising and mapping token strings to integer
+codes — and hands over a raw CSR of codes (``RawSets``: items -> groups -> ids, a group being one
+*part* of the item's value or one explicit *level*).  ``nsm_pack_sets_measure`` /
+``nsm_pack_sets_fill`` (csrc/pack.cu) then build every array of ``nsm_sets_t`` in device memory,
+bit-identical to the numpy packer, and the cohort is ready for ``Engine.all_pairs`` without a
+host round trip of the packed arrays.  No GPU -> raises (``Engine`` does).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from napkon_string_matching.gpu import lib as nsmlib
+from napkon_string_matching.gpu.engine import DeviceCohort, Engine
+from napkon_string_matching.gpu.pack import (HEAD_IDS, SLOT_BLOCK, SLOT_CAP, PackedSets, PackError)
+
+
+@dataclass
+class RawSets:
+    """Dictionary codes of one cohort side: ids of group g are ``ids[grp_id_off[g]:grp_id_off[g+1]]``,
+    groups of item i are ``item_grp_off[i]:item_grp_off[i+1]``.  ``mode`` says what a group is:
+    ``RAW_SUFFIX_PARTS`` — one part of the item's value, level j = id set of the last j+1 parts
+    (``items[-i:]``, /root/reference/napkon_string_matching/types/comparable_data.py:283-285);
+    ``RAW_LEVELS`` — level j itself."""
+    item_grp_off: np.ndarray
+    grp_id_off: np.ndarray
+    ids: np.ndarray
+    mode: int = nsmlib.RAW_SUFFIX_PARTS
+
+    @property
+    def n_items(self) -> int:
+        return len(self.item_grp_off) - 1
+
+    @property
+    def n_groups(self) -> int:
+        return len(self.grp_id_off) - 1
+
+    def max_levels(self) -> int:
+        return int(np.diff(self.item_grp_off.astype(np.int64)).max(initial=0))
+
+
+def _offsets(lens: np.ndarray) -> np.ndarray:
+    off = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    if off[-1] >= 2 ** 32:
+        raise PackError("more than 2^32 rows on one side")
+    return off.astype(np.uint32)
+
+
+def raw_from_parts(part_lens: np.ndarray, flat_ids: np.ndarray) -> RawSets:
+    """Same input convention as :func:`pack.pack_part_id_sets`: ``part_lens[i, q]`` ids of part q
+    of item i follow one another in ``flat_ids``; parts of length 0 are absent."""
+    part_lens = np.asarray(part_lens, dtype=np.int64)
+    present = part_lens > 0
+    return RawSets(_offsets(present.sum(axis=1)), _offsets(part_lens[present]),
+                   np.ascontiguousarray(flat_ids, dtype=np.uint32), nsmlib.RAW_SUFFIX_PARTS)
+
+
+def raw_from_id_lists(lens: np.ndarray, flat_ids: np.ndarray) -> RawSets:
+    """Same input convention as :func:`pack.pack_suffix_id_sets`: item i is a list of ``lens[i]``
+    single-token parts (the ``TokenIds`` column)."""
+    lens = np.asarray(lens, dtype=np.int64)
+    n_ids = int(lens.sum())
+    return RawSets(_offsets(lens), np.arange(n_ids + 1, dtype=np.uint32),
+                   np.ascontiguousarray(flat_ids, dtype=np.uint32), nsmlib.RAW_SUFFIX_PARTS)
+
+
+def raw_from_levels(items_levels: Sequence[Sequence[Sequence[int]]]) -> RawSets:
+    """Explicit levels: ``items_levels[i][j]`` is the code list of level j of item i."""
+    k = [len(lv) for lv in items_levels]
+    sizes = [len(level) for lv in items_levels for level in lv]
+    flat = [c for lv in items_levels for level in lv for c in level]
+    return RawSets(_offsets(np.asarray(k, dtype=np.int64)), _offsets(np.asarray(sizes, dtype=np.int64)),
+                   np.asarray(flat, dtype=np.uint32), nsmlib.RAW_LEVELS)
+
+
+_SETS_FIELDS = ("item_level_off", "level_tok_off", "tok", "tok_entry", "level_head", "level_tail",
+                "level_tail2", "level_info", "item_any", "item_k", "slot_ht", "slot_info")
+
+
+class DevicePacker:
+    """Packs raw code CSRs on the engine's device.  All sides of one comparison must go through
+    one call of :meth:`pack` (they share the frequency ranking, like ``pack.pack_sets``)."""
+
+    def __init__(self, engine: Engine):
+        self.engine = engine
+        self.lib = engine.lib
+        self.device = engine.device
+        self.last_rank: Optional[np.ndarray] = None
+
+    def _dev(self, arr: np.ndarray, dtype) -> torch.Tensor:
+        arr = np.ascontiguousarray(arr, dtype=dtype)
+        if arr.size == 0:
+            arr = np.zeros(1, dtype=dtype)
+        return torch.from_numpy(arr.view(np.uint8).reshape(-1)).to(self.device)
+
+    def _empty(self, n_bytes: int) -> torch.Tensor:
+        return torch.empty(max(int(n_bytes), 16), dtype=torch.uint8, device=self.device)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def frequency_rank(self, raws: List[C.Structure], n_vocab: int) -> np.ndarray:
+        """``pack.frequency_rank`` with the histogram taken on the device: rank[id] = position of
+        id when ids are ordered by falling count over all sides (ties: smaller id first)."""
+        counts = torch.zeros(max(n_vocab, 1), dtype=torch.int32, device=self.device)
+        for st in raws:
+            nsmlib.check(self.lib.nsm_pack_count_ids(C.byref(st), counts.data_ptr(), self._stream()))
+            self.engine.launches += self.lib.nsm_last_launch_count()
+        host = counts.cpu().numpy().view(np.uint32)[:n_vocab].astype(np.int64)
+        order = np.argsort(-host, kind="stable")
+        rank = np.empty(n_vocab, dtype=np.int64)
+        rank[order] = np.arange(n_vocab, dtype=np.int64)
+        return rank
+
+    def pack(self, sides: Sequence[RawSets], n_vocab: int,
+             rank: Union[None, str, np.ndarray] = "frequency") -> List[DeviceCohort]:
+        """``rank``: "frequency" (ids renumbered by falling frequency over all sides, what
+        ``pack.pack_sets`` does), an explicit renumbering array, or None (ids used as they are)."""
+        with torch.cuda.device(self.device):
+            return self._pack(sides, n_vocab, rank)
+
+    def _pack(self, sides, n_vocab, rank):
+        staged = []
+        for raw in sides:
+            if raw.n_items >= 2 ** 32 - 1 or len(raw.ids) >= 2 ** 32:
+                raise PackError("more than 2^32 rows on one side")
+            tensors = [self._dev(raw.item_grp_off, np.uint32), self._dev(raw.grp_id_off, np.uint32),
+                       self._dev(raw.ids, np.uint32)]
+            st = nsmlib.NsmRawSets(tensors[0].data_ptr(), tensors[1].data_ptr(), tensors[2].data_ptr(),
+                                   None, raw.n_items, raw.n_groups, len(raw.ids), n_vocab, raw.mode, 0)
+            staged.append((raw, st, tensors))
+        rank_dev = None
+        if isinstance(rank, str):
+            if rank != "frequency":
+                raise ValueError(rank)
+            rank = self.frequency_rank([st for _, st, _ in staged], n_vocab)
+        if rank is not None:
+            self.last_rank = np.asarray(rank)
+            rank_dev = self._dev(rank, np.uint32)
+        out = []
+        for raw, st, tensors in staged:
+            if rank_dev is not None:
+                st.rank = rank_dev.data_ptr()
+            out.append(self._pack_one(raw, st, n_vocab))
+        return out
+
+    def _pack_one(self, raw: RawSets, st, n_vocab: int) -> DeviceCohort:
+        n, n_levels = raw.n_items, raw.n_groups
+        item_tok_off = self._empty((n + 1) * 4)
+        totals = self._empty(16)
+        scratch_bytes = int(self.lib.nsm_pack_scratch_bytes(n))
+        scratch = self._empty(scratch_bytes)
+        nsmlib.check(self.lib.nsm_pack_sets_measure(C.byref(st), item_tok_off.data_ptr(), totals.data_ptr(),
+                                                    scratch.data_ptr(), scratch_bytes, self._stream()))
+        self.engine.launches += self.lib.nsm_last_launch_count()
+        n_tok, flags = (int(x) for x in totals.cpu().numpy().view(np.uint64)[:2])
+        self._raise_for(flags)
+        if n_tok >= 2 ** 32:
+            raise PackError("more than 2^32 token rows on one side")
+        max_k = raw.max_levels()
+        n_slots = min(max(max_k - 1, 1), SLOT_CAP)
+        stride = max(SLOT_BLOCK, (n + SLOT_BLOCK - 1) // SLOT_BLOCK * SLOT_BLOCK)
+        exact_bits = n_vocab <= 2 * HEAD_IDS
+        sizes = {"item_level_off": (n + 1) * 4, "level_tok_off": (n_levels + 1) * 4, "tok": n_tok * 4,
+                 "tok_entry": n_tok, "level_head": n_levels * 8, "level_tail": n_levels * 8,
+                 "level_tail2": n_levels * 8, "level_info": n_levels * 4, "item_any": n * 16,
+                 "item_k": n * 4, "slot_ht": n_slots * stride * 16, "slot_info": n_slots * stride * 4}
+        tensors = [self._empty(sizes[f]) for f in _SETS_FIELDS]
+        sets = nsmlib.NsmSets(*[t.data_ptr() for t in tensors], n, n_levels, max_k, n_slots,
+                              int(exact_bits), stride, 0, 0)
+        flags_dev = self._empty(4)
+        nsmlib.check(self.lib.nsm_pack_sets_fill(C.byref(st), item_tok_off.data_ptr(), C.byref(sets),
+                                                 flags_dev.data_ptr(), self._stream()))
+        self.engine.launches += self.lib.nsm_last_launch_count()
+        off = item_tok_off.cpu().numpy().view(np.uint32)[: n + 1].astype(np.int64)
+        flags = int(flags_dev.cpu().numpy().view(np.uint32)[0])
+        self._raise_for(flags)
+        sets.nested = int(n_tok == 0 or (not (flags & nsmlib.PACK_FLAG_NOT_NESTED) and max_k <= 255))
+        weights = np.diff(off).astype(np.float64) + 1.0
+        return DeviceCohort("sets", sets, tensors, n, max_k, sum(sizes.values()), weights, None,
+                            n_vocab, sizes)
+
+    @staticmethod
+    def _raise_for(flags: int) -> None:
+        if flags & nsmlib.PACK_FLAG_BAD_ID:
+            raise PackError("a token code is >= n_vocab")
+        if flags & nsmlib.PACK_FLAG_TOO_LARGE:
+            raise PackError(f"an item holds more than {nsmlib.PACK_MAX_ITEM_IDS} ids (or 65535 levels); "
+                            "pack this cohort with gpu.pack on the host")
+
+
+_DTYPES = {"item_level_off": np.uint32, "level_tok_off": np.uint32, "tok": np.uint32,
+           "tok_entry": np.uint8, "level_head": np.uint64, "level_tail": np.uint64,
+           "level_tail2": np.uint64, "level_info": np.uint32, "item_any": np.uint64,
+           "item_k": np.uint32, "slot_ht": np.uint64, "slot_info": np.uint32}
+
+
+def to_host(cohort: DeviceCohort) -> PackedSets:
+    """Copies a device-packed cohort back as a ``PackedSets`` (tests, inspection)."""
+    st = cohort.struct
+    arrays = {}
+    for f, t in zip(_SETS_FIELDS, cohort.tensors):
+        n_bytes = cohort.sizes[f]
+        arrays[f] = t[:n_bytes].cpu().numpy().view(_DTYPES[f]).copy() if n_bytes else \
+            np.zeros(0, dtype=_DTYPES[f])
+    arrays["item_any"] = arrays["item_any"].reshape(-1, 2)
+    arrays["slot_ht"] = arrays["slot_ht"].reshape(st.n_slots, st.slot_stride, 2)
+    arrays["slot_info"] = arrays["slot_info"].reshape(st.n_slots, st.slot_stride)
+    return PackedSets(*[arrays[f] for f in _SETS_FIELDS], cohort.n_vocab, bool(st.exact_bits),
+                      int(st.max_levels), bool(st.nested))

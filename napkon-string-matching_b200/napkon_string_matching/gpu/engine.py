@@ -35,6 +35,8 @@ class DeviceCohort:
     h2d_bytes: int
     weights: np.ndarray             # per-item work estimate, for row-block balancing
     perm: Optional[np.ndarray] = None  # stored position -> caller's item index (strings)
+    n_vocab: int = 0                   # device-packed cohorts (gpu/device_pack.py) ...
+    sizes: Optional[Dict[str, int]] = None  # ... and the byte size of each of their arrays
 
 
 @dataclass
@@ -65,6 +67,16 @@ class Engine:
         self._copy_stream: Optional[torch.cuda.Stream] = None
         self.last_infos: List[Dict] = []
         self.last_info: Dict = {}
+        self._packer = None
+
+    @property
+    def device_packer(self):
+        """Device-side token packing (gpu/device_pack.py), bound to this engine's device."""
+        if self._packer is None:
+            from napkon_string_matching.gpu.device_pack import DevicePacker
+
+            self._packer = DevicePacker(self)
+        return self._packer
 
     # ------------------------------------------------------------------ uploads
     def _to_device(self, arr) -> torch.Tensor:

@@ -19,8 +19,13 @@ STAT_NAMES = ("candidates", "level_evals", "level_merges", "bound_pairs")
 PAIR_DTYPE = np.dtype([("left", np.uint32), ("right", np.uint32), ("score", np.float64)])
 assert PAIR_DTYPE.itemsize == 16
 
+RAW_SUFFIX_PARTS, RAW_LEVELS = 0, 1
+PACK_MAX_ITEM_IDS = 1024
+PACK_FLAG_TOO_LARGE, PACK_FLAG_NOT_NESTED, PACK_FLAG_BAD_ID = 1, 2, 4
+
 EXPORTS = ("nsm_version", "nsm_last_error", "nsm_last_launch_count", "nsm_jaccard_allpairs",
-           "nsm_qratio_allpairs", "nsm_microbench")
+           "nsm_qratio_allpairs", "nsm_microbench", "nsm_pack_count_ids", "nsm_pack_scratch_bytes",
+           "nsm_pack_sets_measure", "nsm_pack_sets_fill")
 
 
 class NsmSets(C.Structure):
@@ -38,6 +43,13 @@ class NsmStrings(C.Structure):
                 ("n_levels", C.c_uint32), ("max_levels", C.c_uint32), ("max_len", C.c_uint32),
                 ("n_alphabet", C.c_uint32), ("reserved_", C.c_uint32),
                 ("class_end", C.c_uint32 * 8)]
+
+
+class NsmRawSets(C.Structure):
+    _fields_ = [("item_grp_off", C.c_void_p), ("grp_id_off", C.c_void_p), ("ids", C.c_void_p),
+                ("rank", C.c_void_p), ("n_items", C.c_uint32), ("n_groups", C.c_uint32),
+                ("n_ids", C.c_uint32), ("n_vocab", C.c_uint32), ("mode", C.c_uint32),
+                ("reserved_", C.c_uint32)]
 
 
 class NsmJob(C.Structure):
@@ -74,6 +86,16 @@ def load() -> C.CDLL:
     lib.nsm_microbench.restype = C.c_int
     lib.nsm_microbench.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
                                    C.POINTER(C.c_uint64), C.c_void_p]
+    lib.nsm_pack_count_ids.restype = C.c_int
+    lib.nsm_pack_count_ids.argtypes = [C.POINTER(NsmRawSets), C.c_void_p, C.c_void_p]
+    lib.nsm_pack_scratch_bytes.restype = C.c_uint64
+    lib.nsm_pack_scratch_bytes.argtypes = [C.c_uint32]
+    lib.nsm_pack_sets_measure.restype = C.c_int
+    lib.nsm_pack_sets_measure.argtypes = [C.POINTER(NsmRawSets), C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_uint64, C.c_void_p]
+    lib.nsm_pack_sets_fill.restype = C.c_int
+    lib.nsm_pack_sets_fill.argtypes = [C.POINTER(NsmRawSets), C.c_void_p, C.POINTER(NsmSets),
+                                       C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
 

@@ -140,6 +140,34 @@ def pack_levels(left_levels, right_levels, score_func: str):
                              pack.fuzzy_level_strings(right_levels))
 
 
+def upload_levels(engine, left_levels, right_levels, score_func: str):
+    """Both sides in device memory, ready for ``engine.all_pairs``: ``(left, right, perms)``.
+
+    Token sets: the host maps token strings to codes (exact string identity, Q3) and the GPU
+    builds the packed arrays (gpu/device_pack.py).  An item beyond the device packer's per-item
+    limit sends the comparison through the numpy packer instead.  Strings are packed on the host
+    (their per-level ``default_process`` is Python string work)."""
+    packer = getattr(engine, "device_packer", None) if KINDS[score_func] == "sets" else None
+    if packer is not None:
+        from napkon_string_matching.gpu.device_pack import RawSets
+
+        parts = [pack._csr_from_nested(s) for s in (left_levels, right_levels)]
+        tokens = [t for _, _, flat in parts for t in flat]
+        codes, uniques = pd.factorize(np.asarray(tokens, dtype=object)) if tokens else (np.zeros(0, np.int64), [])
+        raws, pos = [], 0
+        for item_level_off, level_off, flat in parts:
+            raws.append(RawSets(item_level_off.astype(np.uint32), level_off.astype(np.uint32),
+                                codes[pos:pos + len(flat)].astype(np.uint32), nsmlib.RAW_LEVELS))
+            pos += len(flat)
+        try:
+            dl, dr = packer.pack(raws, len(uniques), rank="frequency")
+            return dl, dr, (None, None)
+        except pack.PackError:
+            pass
+    pl, pr = pack_levels(left_levels, right_levels, score_func)
+    return engine.upload(pl), engine.upload(pr), (getattr(pl, "perm", None), getattr(pr, "perm", None))
+
+
 def score_all_pairs(left_levels, right_levels, score_func: str, score_threshold: float,
                     categories: Optional[dict] = None,
                     skip_pair: Optional[Callable[[int, int], bool]] = None,
@@ -179,14 +207,13 @@ def score_all_pairs(left_levels, right_levels, score_func: str, score_threshold:
     if len(left_levels) == 0 or len(right_levels) == 0:
         return np.zeros(0, dtype=PAIR_DTYPE)
     engine = engine or default_engine()
-    pl, pr = pack_levels(left_levels, right_levels, score_func)
-    dl, dr = engine.upload(pl), engine.upload(pr)
+    dl, dr, (lperm, rperm) = upload_levels(engine, left_levels, right_levels, score_func)
     kw = {}
     if categories is not None and host_cat is None:
         # masks are indexed by stored position (string packs group their items by length class)
         lmask, rmask = categories["left"], categories["right"]
-        if getattr(pl, "perm", None) is not None:
-            lmask, rmask = lmask[pl.perm], rmask[pr.perm]
+        if lperm is not None:
+            lmask, rmask = lmask[lperm], rmask[rperm]
         kw = dict(l_cat=engine.upload_masks(lmask), r_cat=engine.upload_masks(rmask),
                   cat_mode=categories["cat_mode"])
     records = distributed.sharded_all_pairs(

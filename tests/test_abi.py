@@ -37,6 +37,7 @@ def test_struct_layouts_match_the_header():
     assert nsmlib.NsmJob.threshold.offset == 16
     assert nsmlib.NsmJob.out_pairs.offset == 40
     assert ctypes.sizeof(nsmlib.NsmJob) == 80
+    assert ctypes.sizeof(nsmlib.NsmRawSets) == 4 * 8 + 6 * 4
     assert nsmlib.PAIR_DTYPE.itemsize == 16
     assert nsmlib.PAIR_DTYPE.fields["score"][1] == 8
 
