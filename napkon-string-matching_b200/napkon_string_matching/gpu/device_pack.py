@@ -34,6 +34,17 @@ class RawSets:
     grp_id_off: np.ndarray
     ids: np.ndarray
     mode: int = nsmlib.RAW_SUFFIX_PARTS
+    pinned: Optional[List[torch.Tensor]] = None   # page-locked copies of the three arrays (pin())
+
+    def pin(self) -> "RawSets":
+        """Page-locks copies of the arrays so that the upload is one asynchronous DMA each."""
+        self.pinned = [torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint32).view(np.uint8).reshape(-1)
+                                        .copy()).pin_memory() if a.size else None
+                       for a in (self.item_grp_off, self.grp_id_off, self.ids)]
+        return self
+
+    def nbytes(self) -> int:
+        return 4 * (len(self.item_grp_off) + len(self.grp_id_off) + len(self.ids))
 
     @property
     def n_items(self) -> int:
@@ -133,8 +144,10 @@ class DevicePacker:
         for raw in sides:
             if raw.n_items >= 2 ** 32 - 1 or len(raw.ids) >= 2 ** 32:
                 raise PackError("more than 2^32 rows on one side")
-            tensors = [self._dev(raw.item_grp_off, np.uint32), self._dev(raw.grp_id_off, np.uint32),
-                       self._dev(raw.ids, np.uint32)]
+            arrays = (raw.item_grp_off, raw.grp_id_off, raw.ids)
+            pinned = raw.pinned or (None, None, None)
+            tensors = [pin.to(self.device, non_blocking=True) if pin is not None else self._dev(a, np.uint32)
+                       for a, pin in zip(arrays, pinned)]
             st = nsmlib.NsmRawSets(tensors[0].data_ptr(), tensors[1].data_ptr(), tensors[2].data_ptr(),
                                    None, raw.n_items, raw.n_groups, len(raw.ids), n_vocab, raw.mode, 0)
             staged.append((raw, st, tensors))

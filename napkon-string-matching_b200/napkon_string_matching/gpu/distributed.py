@@ -7,6 +7,8 @@ records themselves are concatenated on the host through a gloo group.
 """
 from __future__ import annotations
 
+import contextlib
+import threading
 from typing import Callable, List, Tuple
 
 import numpy as np
@@ -32,10 +34,32 @@ def partition_rows(weights: np.ndarray, parts: int) -> List[Tuple[int, int]]:
     return [(int(a), int(b)) for a, b in zip(cuts[:-1], cuts[1:])]
 
 
+_local = threading.local()
+
+
+@contextlib.contextmanager
+def whole_comparisons():
+    """Inside the block this rank scores every comparison completely by itself: the scheduler
+    (gpu/scheduler.py) has dealt out whole comparisons, so rows are not sharded again."""
+    previous = getattr(_local, "whole", False)
+    _local.whole = True
+    try:
+        yield
+    finally:
+        _local.whole = previous
+
+
 def _world() -> Tuple[int, int]:
+    if getattr(_local, "whole", False):
+        return 0, 1
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
     return 0, 1
+
+
+def host_group():
+    """The gloo group host-side exchanges go through (None: the default group is gloo)."""
+    return _get_host_group()
 
 
 def _get_host_group():

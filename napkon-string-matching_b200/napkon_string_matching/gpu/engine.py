@@ -6,7 +6,9 @@ PyTorch is used for device memory, pinned host memory and streams only.  No GPU 
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
+import threading
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
@@ -347,10 +349,34 @@ class Engine:
 
 
 _default_engine: Optional[Engine] = None
+_thread = threading.local()
 
 
 def default_engine() -> Engine:
+    """The engine the host API scores with: the one bound to this thread by :func:`use_engine`
+    (gpu/scheduler.py runs one worker thread per GPU), else a process-wide engine on the current
+    CUDA device."""
     global _default_engine
+    bound = getattr(_thread, "engine", None)
+    if bound is not None:
+        return bound
     if _default_engine is None:
         _default_engine = Engine()
     return _default_engine
+
+
+@contextlib.contextmanager
+def use_engine(engine):
+    """Binds ``engine`` to the calling thread (and makes its CUDA device the thread's current
+    device, which the C ABI's kernel launches need) for the duration of the block."""
+    previous = getattr(_thread, "engine", None)
+    _thread.engine = engine
+    device = getattr(engine, "device", None)
+    try:
+        if device is not None:
+            with torch.cuda.device(device):
+                yield engine
+        else:
+            yield engine
+    finally:
+        _thread.engine = previous

@@ -15,8 +15,9 @@ import logging
 from itertools import combinations
 from pathlib import Path
 from string import Template
-from typing import Any, Dict
+from typing import Any, Dict, List
 
+from napkon_string_matching.gpu.scheduler import ComparisonTask, run_comparisons
 from napkon_string_matching.types.comparable import ComparisonResults
 from napkon_string_matching.types.gecco_definition import GeccoDefinition, KdsDefinition
 from napkon_string_matching.types.mapping import Mapping
@@ -85,41 +86,57 @@ class Matcher:
         self.results = ComparisonResults()
 
     # ---- steps ------------------------------------------------------------------------
-    def match_gecco_with_questionnaires(self) -> None:
-        for name, questionnaire in self.questionnaires.items():
-            logger.info("compare gecco and %s", name)
-            self.results[f"gecco vs {name}"] = self.gecco.compare(
-                questionnaire,
-                existing_mappings_whitelist=self.mappings_whitelist,
-                existing_mappings_blacklist=self.mappings_blacklist,
-                left_name="gecco",
-                right_name=name,
-                cache_dir=self.cache_dir,
-                **self.config[CONFIG_FIELD_MATCHING],
-            )
+    # Every step first lists its comparisons (same order, names and arguments as the reference's
+    # loops, matcher.py:228-284) and then hands the list to the scheduler, which spreads whole
+    # comparisons over the GPUs of the box and returns the results in list order.
+    def _gecco_tasks(self) -> List[ComparisonTask]:
+        return [ComparisonTask(
+            f"gecco vs {name}", self.gecco, questionnaire,
+            dict(existing_mappings_whitelist=self.mappings_whitelist,
+                 existing_mappings_blacklist=self.mappings_blacklist,
+                 left_name="gecco", right_name=name, cache_dir=self.cache_dir,
+                 **self.config[CONFIG_FIELD_MATCHING]))
+            for name, questionnaire in self.questionnaires.items()]
 
-    def match_questionnaires(self, prefix: str = None, *args, **kwargs) -> None:
+    def _questionnaire_tasks(self, prefix: str = None, **kwargs) -> List[ComparisonTask]:
         """Every unordered cohort pair once, the lower-case-smaller name on the left."""
         names = sorted(self.questionnaires, key=str.lower)
-        for name_first, name_second in combinations(names, 2):
-            logger.info("compare %s %s and %s", prefix if prefix else "", name_first, name_second)
-            matches = self.questionnaires[name_first].compare(
-                self.questionnaires[name_second],
-                existing_mappings_whitelist=self.mappings_whitelist,
-                existing_mappings_blacklist=self.mappings_blacklist,
-                left_name=name_first,
-                right_name=name_second,
-                cache_dir=self.cache_dir,
-                **{**self.config[CONFIG_FIELD_MATCHING], **kwargs},
-            )
-            self.results[f"{prefix if prefix else ''}{name_first} vs {name_second}"] = matches
+        return [ComparisonTask(
+            f"{prefix if prefix else ''}{name_first} vs {name_second}",
+            self.questionnaires[name_first], self.questionnaires[name_second],
+            dict(existing_mappings_whitelist=self.mappings_whitelist,
+                 existing_mappings_blacklist=self.mappings_blacklist,
+                 left_name=name_first, right_name=name_second, cache_dir=self.cache_dir,
+                 **{**self.config[CONFIG_FIELD_MATCHING], **kwargs}))
+            for name_first, name_second in combinations(names, 2)]
+
+    def _variable_tasks(self) -> List[ComparisonTask]:
+        return self._questionnaire_tasks(
+            prefix="var_", compare_column="Variable",
+            score_threshold=self.config[CONFIG_FIELD_MATCHING][CONFIG_VARIABLE_THRESHOLD])
+
+    def _run(self, tasks: List[ComparisonTask]) -> None:
+        for task in tasks:
+            logger.info("compare %s", task.name)
+        for task, result in zip(tasks, run_comparisons(tasks)):
+            self.results[task.name] = result
+
+    def match_gecco_with_questionnaires(self) -> None:
+        self._run(self._gecco_tasks())
+
+    def match_questionnaires(self, prefix: str = None, *args, **kwargs) -> None:
+        self._run(self._questionnaire_tasks(prefix, **kwargs))
 
     def match_questionnaires_variables(self) -> None:
-        self.match_questionnaires(
-            prefix="var_",
-            compare_column="Variable",
-            score_threshold=self.config[CONFIG_FIELD_MATCHING][CONFIG_VARIABLE_THRESHOLD],
-        )
+        self._run(self._variable_tasks())
+
+    def match_steps(self, steps) -> None:
+        """All comparisons of the listed steps ("variables", "gecco", "questionnaires") as ONE
+        batch for the scheduler, so that e.g. nine comparisons keep eight GPUs busy; results are
+        stored in the order the sequential step loop would have produced them."""
+        lists = {"variables": self._variable_tasks, "gecco": self._gecco_tasks,
+                 "questionnaires": self._questionnaire_tasks}
+        self._run([task for step in steps if step in lists for task in lists[step]()])
 
     # ---- reporting --------------------------------------------------------------------
     def _analyse(self) -> Dict[str, Dict[str, str]]:

@@ -22,9 +22,8 @@ _STEPS = {
 
 def match(config: Dict, use_cache=True, matcher: Matcher | None = None) -> Matcher:
     matcher = matcher or create_matcher(config, use_cache)
-    for step in config[CONFIG_FIELD_STEPS]:
-        if step in _STEPS:
-            _STEPS[step](matcher)
+    # the comparisons of all steps are independent: one batch for the multi-GPU scheduler
+    matcher.match_steps([step for step in config[CONFIG_FIELD_STEPS] if step in _STEPS])
     matcher.print_analysis()
     matcher.write_results()
     return matcher

@@ -67,3 +67,29 @@ def test_terminology_get_matches_on_the_gpu(cuda_engine):
 
     terminology_cases.check_all()
     terminology_cases.check_add_tokens()
+
+
+def test_scheduler_threads_on_the_gpu(cuda_engine, tmp_path):
+    """gpu/scheduler.py: comparisons dealt out to worker threads, each with its own Engine (one
+    per visible GPU; two engines on the one GPU when there is only one), give the frames of the
+    sequential loop."""
+    import torch
+
+    import test_scheduler as ts
+    from napkon_string_matching.gpu import scheduler
+    from napkon_string_matching.gpu.engine import Engine
+
+    seq, _ = ts._matcher(tmp_path, "seq")
+    for task in seq._variable_tasks() + seq._gecco_tasks() + seq._questionnaire_tasks():
+        seq.results[task.name] = task.run()
+    n_dev = torch.cuda.device_count()
+    engines = [Engine(k % n_dev) for k in range(max(2, n_dev))]
+    par, _ = ts._matcher(tmp_path, "par")
+    tasks = par._variable_tasks() + par._gecco_tasks() + par._questionnaire_tasks()
+    for task, result in zip(tasks, scheduler.run_comparisons(tasks, engines=engines)):
+        par.results[task.name] = result
+    assert all(e.launches > 0 for e in engines)
+    a, b = ts._frames(seq), ts._frames(par)
+    assert list(a) == list(b)
+    for name in a:
+        assert a[name].equals(b[name]), name
