@@ -45,6 +45,7 @@ constexpr int J_OUT = 48;         // staged output records per warp
 constexpr int J_UNROLL = 6;       // steps of stage B, all straight-line code
 constexpr int J_AUNROLL = 4;      // left items per round of stage A
 constexpr int J_QA = 32 + 32 * J_AUNROLL;  // queue A capacity
+constexpr uint32_t NO_TWO = 0xffffffffu;   // JaccardParams::two_small: the >= 2 bits test is off
 
 struct JaccardParams {
     nsm_sets_t L, R;
@@ -52,6 +53,7 @@ struct JaccardParams {
     float thr_lo;        // filter threshold (see filter_threshold); -inf: everything passes
     uint32_t any_depth;  // D of stage A; 0: use the packed all-level item_any
     uint32_t bound_split;  // stage B tests the bound after this many steps (1..J_UNROLL)
+    uint32_t two_small;    // TWO kernels: a step-1 level of at most this many ids makes its item "wild"
     uint32_t n_lchunks, n_rblocks;
 };
 
@@ -181,7 +183,21 @@ __device__ __forceinline__ uint32_t bound_intersection(const ulonglong2 &A, uint
     return min(__popcll(A.x & B.x) + it, min(ia & 0xffffu, ib & 0xffffu));
 }
 
-template <bool DEEP, int SPLIT>
+// Stage A word of the TWO kernels (depth D = 1, threshold so high that ONE shared token cannot
+// lift a pair over it): x = head bitset of the step-1 level, y = its tail signature folded to 62
+// bits (bits 62, 63 onto 60, 61) plus two flag bits.  An item is "wild" when shared signature
+// bits may undercount shared ids (two of its tail ids share a bit) or when its level is so small
+// that one shared id could be enough; a pair with a wild side is tested for >= 1 shared bit as
+// before, every other pair for >= 2 shared bits.  Left words carry (wild << 63 | 1 << 62), right
+// words (1 << 63 | wild << 62), so that bits 63 / 62 of the AND are the two wild flags.
+__device__ __forceinline__ ulonglong2 two_word(ulonglong2 ht, uint32_t info, uint32_t small, bool left) {
+    const uint64_t low = ht.y & 0x3fffffffffffffffull, top = (ht.y >> 62) << 60;
+    const bool wild = (info >> 16) != 0 || (low & top) != 0 || (info & 0xffffu) <= small;
+    const uint64_t w = wild ? 1ull : 0ull;
+    return make_ulonglong2(ht.x, low | top | (left ? (w << 63) | (1ull << 62) : (1ull << 63) | (w << 62)));
+}
+
+template <bool DEEP, int SPLIT, bool TWO>
 __global__ void __launch_bounds__(JT_THREADS, JT_CTAS)
 jaccard_allpairs_kernel(const JaccardParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -285,6 +301,8 @@ jaccard_allpairs_kernel(const JaccardParams p) {
                 any.x = any.y = ~0ull;
             } else if (p.any_depth == 0) {
                 any = __ldg(reinterpret_cast<const ulonglong2 *>(p.L.item_any) + l0 + li);
+            } else if (TWO) {
+                any = two_word(__ldg(l_slot_ht + l0 + li), __ldg(p.L.slot_info + l0 + li), p.two_small, true);
             } else {
                 for (uint32_t sl = 0; sl < min(p.any_depth, SL); ++sl) {
                     const ulonglong2 ht = __ldg(l_slot_ht + (size_t)sl * p.L.slot_stride + l0 + li);
@@ -296,9 +314,14 @@ jaccard_allpairs_kernel(const JaccardParams p) {
         }
         mbar_wait(&s.bar, bar_parity);  // the right block has landed
         bar_parity ^= 1u;
-        for (uint32_t sl = 0; sl < min(p.any_depth, SR); ++sl) {
-            const ulonglong2 ht = s.r_ht[sl][tid];
-            rany_h |= ht.x; rany_t |= ht.y;
+        if (TWO) {
+            const ulonglong2 w = two_word(s.r_ht[0][tid], s.r_info[0][tid], p.two_small, false);
+            rany_h = w.x; rany_t = w.y;
+        } else {
+            for (uint32_t sl = 0; sl < min(p.any_depth, SR); ++sl) {
+                const ulonglong2 ht = s.r_ht[sl][tid];
+                rany_h |= ht.x; rany_t |= ht.y;
+            }
         }
         if (!r_valid) rany_h = rany_t = 0;
         // threshold <= 0 keeps every pair; an item without levels must reach stage C, which
@@ -320,8 +343,18 @@ jaccard_allpairs_kernel(const JaccardParams p) {
                 for (int u = 0; u < J_AUNROLL; ++u) {
                     const uint32_t li = min(li_next + u, nl - 1);
                     const ulonglong2 lany = s.l_any[li];
-                    pass[u] = r_valid && li_next + u < nl &&
-                              ((lany.x & rany_h) | (lany.y & rany_t)) != 0;
+                    if (TWO) {
+                        // shared bits of the step-1 levels: at least two, or one next to a wild flag
+                        const uint64_t z = lany.x & rany_h, w = lany.y & rany_t;
+                        const uint32_t z0 = (uint32_t)z, z1 = (uint32_t)(z >> 32), w0 = (uint32_t)w,
+                                       w1 = (uint32_t)(w >> 32), wc = w1 & 0x3fffffffu;
+                        const uint32_t zz = z0 | z1, ww = w0 | wc, any1 = zz | ww;
+                        const uint32_t multi = (any1 & (any1 - 1u)) | (z0 & z1) | (w0 & wc) | (zz & ww);
+                        pass[u] = r_valid && li_next + u < nl && any1 != 0 && (multi | (w1 >> 30)) != 0;
+                    } else {
+                        pass[u] = r_valid && li_next + u < nl &&
+                                  ((lany.x & rany_h) | (lany.y & rany_t)) != 0;
+                    }
                     if (p.job.cat_mode)
                         pass[u] = pass[u] && keep_categories(p.job.cat_mode, __ldg(p.job.l_cat + l0 + li), rcat);
                     m[u] = __ballot_sync(FULL_MASK, pass[u]);
@@ -577,14 +610,14 @@ jaccard_allpairs_kernel(const JaccardParams p) {
     }
 }
 
-template <bool DEEP, int SPLIT>
+template <bool DEEP, int SPLIT, bool TWO = false>
 static int launch_jaccard(const JaccardParams &p, uint64_t n_units, cudaStream_t stream) {
     const size_t smem = sizeof(JaccardSmem);
-    NSM_CUDA_CHECK(cudaFuncSetAttribute(jaccard_allpairs_kernel<DEEP, SPLIT>,
+    NSM_CUDA_CHECK(cudaFuncSetAttribute(jaccard_allpairs_kernel<DEEP, SPLIT, TWO>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint64_t resident = (uint64_t)JT_CTAS * (uint64_t)sm_count();
     const uint32_t grid = (uint32_t)(n_units < resident ? n_units : resident);
-    jaccard_allpairs_kernel<DEEP, SPLIT><<<grid, JT_THREADS, smem, stream>>>(p);
+    jaccard_allpairs_kernel<DEEP, SPLIT, TWO><<<grid, JT_THREADS, smem, stream>>>(p);
     count_launch();
     NSM_CUDA_CHECK(cudaGetLastError());
     return NSM_OK;
@@ -593,7 +626,8 @@ static int launch_jaccard(const JaccardParams &p, uint64_t n_units, cudaStream_t
 template <bool DEEP>
 static int launch_jaccard_split(const JaccardParams &p, uint64_t n_units, cudaStream_t stream) {
     switch (p.bound_split) {
-        case 1: return launch_jaccard<DEEP, 1>(p, n_units, stream);
+        case 1: return p.two_small != NO_TWO ? launch_jaccard<DEEP, 1, true>(p, n_units, stream)
+                                             : launch_jaccard<DEEP, 1>(p, n_units, stream);
         case 2: return launch_jaccard<DEEP, 2>(p, n_units, stream);
         default: return launch_jaccard<DEEP, J_UNROLL>(p, n_units, stream);
     }
@@ -634,6 +668,7 @@ extern "C" int nsm_jaccard_allpairs(const nsm_sets_t *left, const nsm_sets_t *ri
     // union; stage B tests its bound for the first time after D steps.
     p.any_depth = 0;
     p.bound_split = J_UNROLL;
+    p.two_small = NO_TWO;
     if (p.thr_lo > 0.0f && !job->flat) {
         const uint32_t kmax = left->max_levels > right->max_levels ? left->max_levels : right->max_levels;
         const float w_last = kmax < 120 ? ldexpf(1.0f, -(int)kmax) : 0.0f;
@@ -643,6 +678,17 @@ extern "C" int nsm_jaccard_allpairs(const nsm_sets_t *left, const nsm_sets_t *ri
             p.any_depth = d < (uint32_t)J_SLOTS ? d : (uint32_t)J_SLOTS;
         // splitting pays when few pairs survive the first half, i.e. at high thresholds (small D)
         p.bound_split = d <= 2 ? d : (uint32_t)J_UNROLL;
+        // D == 1: score <= J_1 / 2 + (1/2 - 2^-Kmax), so a kept pair has J_1 >= jmin.  With at most
+        // ONE shared id J_1 <= 1 / (a + b - 1), which is below jmin once a + b > 1 + 1 / jmin: if
+        // both step-1 levels hold more than c = floor(floor(1 + 1/jmin) / 2) ids, a pair needs two
+        // shared ids, hence (signature bits being injective for non-wild items) two shared bits.
+        if (p.any_depth == 1 && p.bound_split == 1) {
+            const double jmin = 2.0 * ((double)p.thr_lo - 0.5 + (double)w_last);
+            if (jmin > 0.0) {
+                const double t = floor((1.0 + 1.0 / jmin) * (1.0 + 1e-9));
+                if (t < 64.0) p.two_small = (uint32_t)t / 2u;
+            }
+        }
     }
     const uint32_t n_rows = job->l_row_end - job->l_row_begin;
     p.n_lchunks = (n_rows + J_UNIT_LEFT - 1) / J_UNIT_LEFT;

@@ -175,6 +175,12 @@ class Engine:
         keeps more than ``max_pairs_per_block`` records is split into left row blocks.
         ``to_host=False`` leaves the records on the device (kernel-only timing) and returns empty
         arrays; ``copy=False`` returns views of the pinned arena (valid until the next call)."""
+        # the C ABI launches on the calling thread's current device: make it this engine's
+        with torch.cuda.device(self.device):
+            return self._run_jobs(jobs, capacity, to_host, copy)
+
+    def _run_jobs(self, jobs: List["Job"], capacity: Optional[int], to_host: bool, copy: bool
+                  ) -> List[np.ndarray]:
         stream = torch.cuda.current_stream(self.device)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
@@ -330,6 +336,7 @@ class Engine:
                    threads: int = 256) -> float:
         """Measured 32-bit integer ops/s of one instruction kind (see nsm_microbench)."""
         sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        torch.cuda.set_device(self.device)
         blocks = sms * blocks_per_sm
         sink = torch.zeros(4, dtype=torch.int32, device=self.device)
         ops = C.c_uint64(0)

@@ -69,7 +69,7 @@ def test_terminology_get_matches_on_the_gpu(cuda_engine):
     terminology_cases.check_add_tokens()
 
 
-def test_scheduler_threads_on_the_gpu(cuda_engine, tmp_path):
+def test_scheduler_threads_on_the_gpu(engine, tmp_path):
     """gpu/scheduler.py: comparisons dealt out to worker threads, each with its own Engine (one
     per visible GPU; two engines on the one GPU when there is only one), give the frames of the
     sequential loop."""
@@ -79,9 +79,12 @@ def test_scheduler_threads_on_the_gpu(cuda_engine, tmp_path):
     from napkon_string_matching.gpu import scheduler
     from napkon_string_matching.gpu.engine import Engine
 
+    from napkon_string_matching.gpu.engine import use_engine
+
     seq, _ = ts._matcher(tmp_path, "seq")
-    for task in seq._variable_tasks() + seq._gecco_tasks() + seq._questionnaire_tasks():
-        seq.results[task.name] = task.run()
+    with use_engine(engine):
+        for task in seq._variable_tasks() + seq._gecco_tasks() + seq._questionnaire_tasks():
+            seq.results[task.name] = task.run()
     n_dev = torch.cuda.device_count()
     engines = [Engine(k % n_dev) for k in range(max(2, n_dev))]
     par, _ = ts._matcher(tmp_path, "par")

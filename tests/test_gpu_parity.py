@@ -346,3 +346,27 @@ def test_unsupported_inputs_raise_instead_of_falling_back(engine):
     assert sorted(out["score"].tolist()) == [1 / 60000, 30000 / 60001]
     pl, pr = pack.pack_strings([["ab" * 256]], [["ba" * 256], ["a" * 512]])
     check_against_oracle(engine, pl, pr, 0.0, flat=True)
+
+
+@pytest.mark.parametrize("vocab,max_k,per_part", [(90, 4, 5), (400, 4, 9), (3000, 3, 30), (20000, 4, 6)])
+def test_jaccard_two_shared_bits_filter_vs_oracle(engine, vocab, max_k, per_part):
+    """High thresholds with depth D = 1 run the kernels whose stage A asks for TWO shared
+    signature bits unless a side is "wild" (tail ids sharing a signature bit, or a step-1 level so
+    small that one shared id could suffice).  Dense vocabularies (many shared ids, many folded
+    tail bits), tiny levels and every threshold region around 1/2 must match the oracle."""
+    rng = np.random.default_rng(vocab + per_part)
+
+    def suffix_items(n):
+        out = []
+        for _ in range(n):
+            parts = [[f"w{int(x)}" for x in rng.zipf(1.2, size=int(rng.integers(1, per_part + 1))) % vocab]
+                     for _ in range(int(rng.integers(1, max_k + 1)))]
+            out.append([sorted({w for part in parts[-j:] for w in part}) for j in range(1, len(parts) + 1)])
+        return out
+
+    pl, pr = pack.pack_sets(suffix_items(500), suffix_items(620))
+    kept = 0
+    for thr in (0.4376, 0.5, 0.5001, 0.5625, 0.6, 0.75, 0.875, 0.9375, 0.95):
+        out, info = check_against_oracle(engine, pl, pr, thr)
+        kept += len(out)
+    assert kept > 0
