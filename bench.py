@@ -556,7 +556,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         alg_bytes = in_bytes + 16 * kept
         sec_step_hbm = kernel_sec_step
-        cpu_val, cpu_sample = cpu_reference(wl, raw, pairs, 12.0, 1, packs)
+        if args.quick:   # kernel experiments: no CPU baseline leg (not a bench line to report)
+            cpu_val, cpu_sample = None, "skipped (--quick)"
+        else:
+            cpu_val, cpu_sample = cpu_reference(wl, raw, pairs, 12.0, 1, packs)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
@@ -604,6 +607,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="tokenids50k", choices=sorted(WORKLOADS))
+    ap.add_argument("--quick", action="store_true",
+                    help="skip the CPU baseline leg (kernel experiments and ncu captures only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -77,14 +77,17 @@ __device__ __forceinline__ uint32_t lcs_bitparallel(const uint64_t *__restrict__
     uint64_t S[W];
 #pragma unroll
     for (int x = 0; x < W; ++x) S[x] = ~0ull;
-    const uint64_t *text8 = reinterpret_cast<const uint64_t *>(text);
-    const size_t row_stride = (size_t)W * nthr;
+    const uint2 *text8 = reinterpret_cast<const uint2 *>(text);
+    // byte addressing: the mask row of character c starts c * row_bytes after my column, so a
+    // character costs one byte extract (PRMT), one multiply-add and the load
+    const unsigned char *col = reinterpret_cast<const unsigned char *>(pm);
+    const uint32_t word_bytes = nthr * 8u, row_bytes = (uint32_t)W * word_bytes;
     auto step = [&](uint32_t c) {
-        const uint64_t *row = pm + c * row_stride;
+        const unsigned char *row = col + c * row_bytes;
         uint32_t carry = 0;
 #pragma unroll
         for (int x = 0; x < W; ++x) {
-            const uint64_t M = row[(size_t)x * nthr];
+            const uint64_t M = *reinterpret_cast<const uint64_t *>(row + (uint32_t)x * word_bytes);
             const uint64_t u = S[x] & M;
             const uint64_t sum = S[x] + u;
             const uint64_t sum2 = sum + carry;
@@ -96,13 +99,16 @@ __device__ __forceinline__ uint32_t lcs_bitparallel(const uint64_t *__restrict__
     };
     uint32_t j = 0;
     for (; j + 8 <= n; j += 8) {  // eight characters per shared-memory word
-        const uint64_t w8 = text8[j >> 3];
+        const uint2 w8 = text8[j >> 3];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) step((uint32_t)(w8 >> (8 * q)) & 0xffu);
+        for (int q = 0; q < 4; ++q) step(__byte_perm(w8.x, 0u, 0x4440u + q));
+#pragma unroll
+        for (int q = 0; q < 4; ++q) step(__byte_perm(w8.y, 0u, 0x4440u + q));
     }
     if (j < n) {
-        const uint64_t w8 = text8[j >> 3];
-        for (uint32_t q = 0; j + q < n; ++q) step((uint32_t)(w8 >> (8 * q)) & 0xffu);
+        const uint2 w8 = text8[j >> 3];
+        for (uint32_t q = 0; j + q < n; ++q)
+            step(__byte_perm(q < 4 ? w8.x : w8.y, 0u, 0x4440u + (q & 3u)));
     }
     uint32_t lcs = 0;
 #pragma unroll
