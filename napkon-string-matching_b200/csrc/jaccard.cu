@@ -73,6 +73,29 @@ struct __align__(16) JaccardSmem {
     uint64_t bar;  // mbarrier of the right block's bulk copies
 };
 
+// len(A & B) / len(A | B) as the correctly rounded float64 quotient of two small integers without
+// the general division sequence: r = RN(1 / u) from a table, q0 = RN(i * r), e = RN(i - q0 * u)
+// (one FMA), q = RN(q0 + e * r) (one FMA).  q equals RN(i / u) for every 0 <= i <= u <= 255 —
+// checked exhaustively with exact rational arithmetic (tests/test_oracle.py); larger unions
+// take __ddiv_rn.
+struct RcpTable {
+    double v[256];
+    constexpr RcpTable() : v() {
+        for (int u = 1; u < 256; ++u) v[u] = 1.0 / (double)u;
+    }
+};
+__device__ const RcpTable g_rcp = RcpTable();
+
+__device__ __forceinline__ double div_counts(uint32_t i, uint32_t u) {
+    const double a = (double)i, b = (double)u;
+    if (u < 256u) {
+        const double r = g_rcp.v[u];
+        const double q0 = __dmul_rn(a, r);
+        return __fma_rn(__fma_rn(-q0, b, a), r, q0);
+    }
+    return __ddiv_rn(a, b);
+}
+
 __device__ __forceinline__ float pow2_neg(uint32_t k) {  // 2^-k, 0 when it underflows fp32
     return k <= 126 ? __int_as_float((127 - (int)k) << 23) : 0.0f;
 }
@@ -572,7 +595,7 @@ jaccard_allpairs_kernel(const JaccardParams p) {
                         w *= 0.5;
                         if (inter) {
                             // len(A & B) / len(A | B): int / int true division; score += s * w
-                            score = __fma_rn(__ddiv_rn((double)inter, (double)uni), w, score);
+                            score = __fma_rn(div_counts(inter, uni), w, score);
                         } else if (uni == 0) {  // 0 / 0: ZeroDivisionError upstream
                             atomicOr(p.job.out_flags, NSM_FLAG_ZERO_UNION);
                             ok = false;

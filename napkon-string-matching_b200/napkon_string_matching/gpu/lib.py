@@ -3,12 +3,14 @@ if the library or a CUDA device is missing, loading raises."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 import pathlib
 
 import numpy as np
 
 _HERE = pathlib.Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libnsm_b200.so"
+# NSM_B200_LIB points at another build of the same library (kernel A/B experiments)
+LIB_PATH = pathlib.Path(os.environ.get("NSM_B200_LIB") or _HERE / "libnsm_b200.so")
 
 NSM_OK = 0
 FLAG_OVERFLOW, FLAG_ZERO_UNION, FLAG_EMPTY_ITEM = 1, 2, 4

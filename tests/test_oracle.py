@@ -201,3 +201,20 @@ def test_pack_limits_are_loud():
         pack.pack_sets([[[f"t{i}" for i in range(70000)]]])
     (p,) = pack.pack_strings([["x" * 600], ["y"]])   # longer than the kernel's 8 words: last class
     assert int(p.class_end[-1]) == 1 and p.n_items == 2
+
+
+def test_reciprocal_fma_division_equals_true_division_for_small_counts():
+    """csrc/jaccard.cu:div_counts computes |A & B| / |A | B| as r = RN(1/u); q0 = RN(i*r);
+    q = fma(fma(-q0, u, i), r, q0) for u <= 255.  Emulated here with exact rational arithmetic
+    (one rounding per fused operation): it must equal Python's correctly rounded i / u, which is
+    what score_functions.py:13 returns, for every 0 <= i <= u <= 255."""
+    from fractions import Fraction
+
+    for u in range(1, 256):
+        r = 1.0 / u
+        for i in range(u + 1):
+            a, b = float(i), float(u)
+            q0 = a * r
+            e = float(Fraction(a) - Fraction(q0) * Fraction(b))
+            q = float(Fraction(q0) + Fraction(e) * Fraction(r))
+            assert q == a / b, (i, u)
