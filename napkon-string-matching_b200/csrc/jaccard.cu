@@ -532,14 +532,64 @@ jaccard_allpairs_kernel(const JaccardParams p) {
                         if ((int)lane == src) { tail_steps = c; ++st_merges; }
                     }
                 }
-                // the left summaries come through L2: keep the loads of the next two steps in
-                // flight while the current step is scored
                 const uint32_t kl1 = max(kl, 1u);
+                // Fast path (warp-uniform): no lane needs a per-level token intersection inside
+                // the step loop (exact tail bits, or the tail counts of all steps are already in
+                // tail_steps).  The steps are then independent of one another up to the final
+                // accumulation, so they are scored two at a time with all loads issued first and
+                // the left summaries of the next two steps in flight; only the float64
+                // accumulation runs in step order, as in the reference.
+                const bool fast_warp = __all_sync(FULL_MASK, exact_bits || nest_ok || kmax == 0);
+                if (fast_warp) {
+                    bool zero_union = false;
+                    ulonglong2 An[2];
+                    uint32_t ian[2];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) An[q] = left_level(c_l, 1 + q, kl1, ian[q]);
+                    for (uint32_t t0 = 1; t0 <= kmax_warp; t0 += 2) {
+                        ulonglong2 A[2], B[2];
+                        uint32_t ia[2], ib[2];
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            A[q] = An[q]; ia[q] = ian[q];
+                            B[q] = right_level(rc, c_r, t0 + q, c_kr, ib[q]);
+                        }
+                        if (t0 + 2 <= kmax_warp) {
+#pragma unroll
+                            for (int q = 0; q < 2; ++q) An[q] = left_level(c_l, t0 + 2 + q, kl1, ian[q]);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const uint32_t t = t0 + q;
+                            uint32_t it = __popcll(A[q].x & B[q].x);
+                            const uint64_t tb = A[q].y & B[q].y;
+                            if (exact_bits) {
+                                it += __popcll(tb);
+                            } else if (tb && t <= 16) {
+                                it += (uint32_t)((t <= 8 ? tail_steps.x >> (8 * (t - 1))
+                                                         : tail_steps.y >> (8 * (t - 9))) & 0xffu);
+                            }
+                            const uint32_t un = (ia[q] & 0xffffu) + (ib[q] & 0xffffu) - it;
+                            if (t <= kmax) {
+                                ++st_evals;
+                                w *= 0.5;
+                                if (it) score = __fma_rn(div_counts(it, un), w, score);
+                                else zero_union |= un == 0;  // 0 / 0: ZeroDivisionError upstream
+                            }
+                        }
+                    }
+                    if (zero_union) {
+                        atomicOr(p.job.out_flags, NSM_FLAG_ZERO_UNION);
+                        ok = false;
+                    }
+                }
+                // General path: the left summaries come through L2: keep the loads of the next
+                // two steps in flight while the current step is scored
                 uint32_t ia1 = 0, ia2 = 0;
                 ulonglong2 A1 = make_ulonglong2(0, 0), A2 = A1;
-                if (kmax_warp >= 1) A1 = left_level(c_l, 1, kl1, ia1);
-                if (kmax_warp >= 2) A2 = left_level(c_l, 2, kl1, ia2);
-                for (uint32_t t = 1; t <= kmax_warp; ++t) {
+                if (!fast_warp && kmax_warp >= 1) A1 = left_level(c_l, 1, kl1, ia1);
+                if (!fast_warp && kmax_warp >= 2) A2 = left_level(c_l, 2, kl1, ia2);
+                for (uint32_t t = 1; !fast_warp && t <= kmax_warp; ++t) {
                     const bool on = t <= kmax;
                     const uint32_t jl = flat ? 0u : min(t, kl - 1), jr = flat ? 0u : min(t, c_kr - 1);
                     bool need = false;
