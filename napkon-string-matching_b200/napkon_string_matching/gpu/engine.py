@@ -55,11 +55,14 @@ class Job:
 
 
 class Engine:
+    PIPELINE_BLOCK_BYTES = 512 << 20
+
     def __init__(self, device: Optional[int] = None, max_pairs_per_block: int = 1 << 30):
         _require_cuda()
         self.lib = nsmlib.load()
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         self.max_pairs_per_block = int(max_pairs_per_block)
+        self.pipeline_d2h = True    # probe + row blocks for results that go to the host
         self._buffers: Dict[str, torch.Tensor] = {}
         self.launches = 0           # kernels of ours launched so far
         self.time_kernels = False   # bracket every comparison kernel with CUDA events
@@ -189,7 +192,11 @@ class Engine:
         ctl_pin = [self._arena(f"ctl_pin{i}", 64, pinned=True) for i in range(2)]
         slot_free: List[Optional[torch.cuda.Event]] = [None, None]   # D2H out of the arena done
 
-        # expand jobs into row-block work items: (job index, begin, end)
+        # expand jobs into row-block work items: (job index, begin, end).  A job whose records go
+        # to the host starts with a PROBE block (1/8 of its rows): its kept-pair density decides
+        # into how many blocks the rest is cut, so that the device->host copy of a large result
+        # starts early and runs beside the remaining kernels instead of after one long launch.
+        probes = set()
         work: List[Tuple[int, int, int]] = []
         infos = []
         for j, job in enumerate(jobs):
@@ -200,7 +207,13 @@ class Engine:
                           "stats": dict.fromkeys(nsmlib.STAT_NAMES, 0),
                           "item_pairs": max(0, end - begin) * job.right.n_items, "parts": []})
             if end > begin and job.right.n_items:
-                work.append((j, begin, end))
+                rows = end - begin
+                if to_host and self.pipeline_d2h and rows >= 8 * 1024 and capacity is None:
+                    cut = begin + rows // 8
+                    probes.add((j, begin, cut))
+                    work += [(j, begin, cut), (j, cut, end)]
+                else:
+                    work.append((j, begin, end))
         self.last_infos = infos
 
         def launch(slot: int, item: Tuple[int, int, int], cap: int):
@@ -270,6 +283,17 @@ class Engine:
                 pending = None
                 slot = p_slot
                 continue
+            if p_item in probes and queue and queue[0][0] == j:
+                # cut the rest of the job into blocks of about PIPELINE_BLOCK_BYTES of records
+                _, rest_b, rest_e = queue.pop(0)
+                density = count / max(1, re_ - rb)
+                expect = density * (rest_e - rest_b) * 16
+                n_parts = int(min(16, max(1, -(-expect // self.PIPELINE_BLOCK_BYTES))))
+                cuts = np.linspace(rest_b, rest_e, n_parts + 1).astype(np.int64)
+                queue[:0] = [(j, int(a), int(b)) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+                if n_parts > 1 or cap_hint is None:
+                    need = int(density * (int(cuts[1]) - int(cuts[0])) * 1.1) + 4096
+                    cap_hint = max(cap_hint or 0, min(self.max_pairs_per_block, need))
             # launch the next job before copying this one out, so that the two overlap
             if queue:
                 item = queue.pop(0)

@@ -370,3 +370,33 @@ def test_jaccard_two_shared_bits_filter_vs_oracle(engine, vocab, max_k, per_part
         out, info = check_against_oracle(engine, pl, pr, thr)
         kept += len(out)
     assert kept > 0
+
+
+def test_pipelined_row_blocks_give_the_same_records(engine):
+    """Results that go to the host are produced as a probe block plus row blocks sized by the
+    probe's density (Engine._run_jobs), so that the copy-out overlaps the remaining kernels.  The
+    records must be those of the single launch, for dense and for sparse results."""
+    lens, flat = syn.token_id_level_sets(20000, 31)
+    pl = pack.pack_suffix_id_sets(lens, flat, 30000)
+    lens, flat = syn.token_id_level_sets(3000, 32)
+    pr = pack.pack_suffix_id_sets(lens, flat, 30000)
+    dl, dr = engine.upload(pl), engine.upload(pr)
+    key = lambda a: a[np.lexsort((a["right"], a["left"]))]
+    old = engine.pipeline_d2h, engine.PIPELINE_BLOCK_BYTES
+    try:
+        for thr in (0.1, 0.7):
+            engine.pipeline_d2h = False
+            want = key(engine.all_pairs(dl, dr, thr))
+            assert engine.last_info["blocks"] == 1
+            engine.pipeline_d2h = True
+            for block_bytes in (1 << 20, 512 << 20):
+                engine.PIPELINE_BLOCK_BYTES = block_bytes
+                got = key(engine.all_pairs(dl, dr, thr))
+                assert engine.last_info["blocks"] >= 2 and engine.last_info["count"] == len(want)
+                assert np.array_equal(got, want)
+            # a row range of the left cohort goes through the same path
+            engine.PIPELINE_BLOCK_BYTES = 1 << 20
+            part = key(engine.all_pairs(dl, dr, thr, rows=(1000, 19000)))
+            assert np.array_equal(part, want[(want["left"] >= 1000) & (want["left"] < 19000)])
+    finally:
+        engine.pipeline_d2h, engine.PIPELINE_BLOCK_BYTES = old
