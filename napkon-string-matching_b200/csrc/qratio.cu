@@ -69,6 +69,75 @@ __host__ __device__ inline QratioLayout qratio_layout(uint32_t n_alpha, uint32_t
     return l;
 }
 
+// sum = S + u over W 64-bit words as ONE multi-word addition: the carry runs through the
+// hardware carry flag (add.cc / addc.cc on the 32-bit halves), two instructions per word instead
+// of an add plus compares and selects per word.  HALVES = 2 * words of one block (<= 8).
+__device__ __forceinline__ uint32_t lo32(uint64_t v) { return (uint32_t)v; }
+__device__ __forceinline__ uint32_t hi32(uint64_t v) { return (uint32_t)(v >> 32); }
+__device__ __forceinline__ uint64_t mk64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
+// one block of two words; carry_in / carry_out are 0 or 1
+__device__ __forceinline__ void add2(const uint64_t *a, const uint64_t *b, uint64_t *r, uint32_t cin,
+                                     uint32_t &cout) {
+    uint32_t r0, r1, r2, r3, t;  // t: scratch of the flag-setting add
+    asm("{\n\t"
+        "add.cc.u32 %5, %14, 0xffffffff;\n\t"   // carry flag = carry_in
+        "addc.cc.u32 %0, %6, %10;\n\t"
+        "addc.cc.u32 %1, %7, %11;\n\t"
+        "addc.cc.u32 %2, %8, %12;\n\t"
+        "addc.cc.u32 %3, %9, %13;\n\t"
+        "addc.u32 %4, 0, 0;\n\t"
+        "}"
+        : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(cout), "=r"(t)
+        : "r"(lo32(a[0])), "r"(hi32(a[0])), "r"(lo32(a[1])), "r"(hi32(a[1])),
+          "r"(lo32(b[0])), "r"(hi32(b[0])), "r"(lo32(b[1])), "r"(hi32(b[1])), "r"(cin));
+    (void)t;
+    r[0] = mk64(r0, r1); r[1] = mk64(r2, r3);
+}
+
+// two words, no carry in, no carry out (the whole pattern of the W = 2 class)
+__device__ __forceinline__ void add2_only(const uint64_t *a, const uint64_t *b, uint64_t *r) {
+    uint32_t r0, r1, r2, r3;
+    asm("{\n\t"
+        "add.cc.u32 %0, %4, %8;\n\t"
+        "addc.cc.u32 %1, %5, %9;\n\t"
+        "addc.cc.u32 %2, %6, %10;\n\t"
+        "addc.u32 %3, %7, %11;\n\t"
+        "}"
+        : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+        : "r"(lo32(a[0])), "r"(hi32(a[0])), "r"(lo32(a[1])), "r"(hi32(a[1])),
+          "r"(lo32(b[0])), "r"(hi32(b[0])), "r"(lo32(b[1])), "r"(hi32(b[1])));
+    r[0] = mk64(r0, r1); r[1] = mk64(r2, r3);
+}
+
+// one word with carry in and out
+__device__ __forceinline__ void add1(uint64_t a, uint64_t b, uint64_t &r, uint32_t cin, uint32_t &cout) {
+    uint32_t r0, r1, t;
+    asm("{\n\t"
+        "add.cc.u32 %3, %8, 0xffffffff;\n\t"
+        "addc.cc.u32 %0, %4, %6;\n\t"
+        "addc.cc.u32 %1, %5, %7;\n\t"
+        "addc.u32 %2, 0, 0;\n\t"
+        "}"
+        : "=r"(r0), "=r"(r1), "=r"(cout), "=r"(t)
+        : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)), "r"(cin));
+    r = mk64(r0, r1);
+}
+
+template <int W>
+__device__ __forceinline__ void add_words(const uint64_t (&a)[W], const uint64_t (&b)[W], uint64_t (&r)[W]) {
+    if (W == 1) {
+        r[0] = a[0] + b[0];
+    } else if (W == 2) {
+        add2_only(a, b, r);
+    } else {
+        uint32_t carry = 0;
+#pragma unroll
+        for (int x = 0; x + 2 <= W; x += 2) add2(a + x, b + x, r + x, carry, carry);
+        if (W & 1) add1(a[W - 1], b[W - 1], r[W - 1], carry, carry);
+    }
+}
+
 // LCS length of my pattern (masks in shared memory, column `pm`) and a text of n characters that
 // starts 8-byte aligned at `text` in shared memory.  Uniform over the CTA.
 template <int W>
@@ -84,18 +153,17 @@ __device__ __forceinline__ uint32_t lcs_bitparallel(const uint64_t *__restrict__
     const uint32_t word_bytes = nthr * 8u, row_bytes = (uint32_t)W * word_bytes;
     auto step = [&](uint32_t c) {
         const unsigned char *row = col + c * row_bytes;
-        uint32_t carry = 0;
+        uint64_t M[W], u[W], sum[W];
 #pragma unroll
         for (int x = 0; x < W; ++x) {
-            const uint64_t M = *reinterpret_cast<const uint64_t *>(row + (uint32_t)x * word_bytes);
-            const uint64_t u = S[x] & M;
-            const uint64_t sum = S[x] + u;
-            const uint64_t sum2 = sum + carry;
-            if (W > 1) carry = (sum < u) | (sum2 < sum);
-            // u is a subset of S, so S - u == S & ~M: one three-input logic op per half instead
-            // of a subtract with borrow
-            S[x] = sum2 | (S[x] & ~M);
+            M[x] = *reinterpret_cast<const uint64_t *>(row + (uint32_t)x * word_bytes);
+            u[x] = S[x] & M[x];
         }
+        add_words<W>(S, u, sum);
+        // u is a subset of S, so S - u == S & ~M: one three-input logic op per half instead of a
+        // subtract with borrow
+#pragma unroll
+        for (int x = 0; x < W; ++x) S[x] = sum[x] | (S[x] & ~M[x]);
     };
     uint32_t j = 0;
     for (; j + 8 <= n; j += 8) {  // eight characters per shared-memory word
@@ -115,6 +183,74 @@ __device__ __forceinline__ uint32_t lcs_bitparallel(const uint64_t *__restrict__
     for (int x = 0; x < W; ++x) lcs += __popcll(~S[x]);
     return lcs;
 }
+
+// Two texts against my pattern at once: the two S chains are independent, so their dependent
+// AND -> ADD -> OR sequences interleave and hide each other's latency (a CTA holds few warps when
+// the mask tables are large).  The texts run in lockstep over the length of the shorter one; the
+// rest of each is finished by itself.
+template <int W>
+__device__ __forceinline__ void lcs_bitparallel2(const uint64_t *__restrict__ pm, uint32_t nthr,
+                                                 const uint8_t *__restrict__ text_a, uint32_t na,
+                                                 const uint8_t *__restrict__ text_b, uint32_t nb,
+                                                 uint32_t &lcs_a, uint32_t &lcs_b) {
+    uint64_t Sa[W], Sb[W];
+#pragma unroll
+    for (int x = 0; x < W; ++x) Sa[x] = Sb[x] = ~0ull;
+    const uint2 *a8 = reinterpret_cast<const uint2 *>(text_a), *b8 = reinterpret_cast<const uint2 *>(text_b);
+    const unsigned char *col = reinterpret_cast<const unsigned char *>(pm);
+    const uint32_t word_bytes = nthr * 8u, row_bytes = (uint32_t)W * word_bytes;
+    auto step = [&](uint64_t (&S)[W], uint32_t c) {
+        const unsigned char *row = col + c * row_bytes;
+        uint64_t M[W], u[W], sum[W];
+#pragma unroll
+        for (int x = 0; x < W; ++x) {
+            M[x] = *reinterpret_cast<const uint64_t *>(row + (uint32_t)x * word_bytes);
+            u[x] = S[x] & M[x];
+        }
+        add_words<W>(S, u, sum);
+#pragma unroll
+        for (int x = 0; x < W; ++x) S[x] = sum[x] | (S[x] & ~M[x]);
+    };
+    const uint32_t nc = min(na, nb);
+    uint32_t j = 0;
+    for (; j + 8 <= nc; j += 8) {
+        const uint2 wa = a8[j >> 3], wb = b8[j >> 3];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            step(Sa, __byte_perm(wa.x, 0u, 0x4440u + q));
+            step(Sb, __byte_perm(wb.x, 0u, 0x4440u + q));
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            step(Sa, __byte_perm(wa.y, 0u, 0x4440u + q));
+            step(Sb, __byte_perm(wb.y, 0u, 0x4440u + q));
+        }
+    }
+    auto finish = [&](uint64_t (&S)[W], const uint2 *t8, uint32_t n) {
+        uint32_t i = j;
+        for (; i + 8 <= n; i += 8) {
+            const uint2 w8 = t8[i >> 3];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) step(S, __byte_perm(w8.x, 0u, 0x4440u + q));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) step(S, __byte_perm(w8.y, 0u, 0x4440u + q));
+        }
+        if (i < n) {
+            const uint2 w8 = t8[i >> 3];
+            for (uint32_t q = 0; i + q < n; ++q)
+                step(S, __byte_perm(q < 4 ? w8.x : w8.y, 0u, 0x4440u + (q & 3u)));
+        }
+    };
+    finish(Sa, a8, na);
+    finish(Sb, b8, nb);
+    lcs_a = lcs_b = 0;
+#pragma unroll
+    for (int x = 0; x < W; ++x) { lcs_a += __popcll(~Sa[x]); lcs_b += __popcll(~Sb[x]); }
+}
+
+#ifndef Q_DUAL
+#define Q_DUAL 1   // score two left strings per round where the registers allow it (W <= 4)
+#endif
 
 // QRatio(a, b) / 100 from the counts: 0 when either processed string is empty, else
 // ((1.0 - dist / lensum) * 100) / 100 with dist = lensum - 2 LCS — this exact operation order.
@@ -212,19 +348,14 @@ qratio_allpairs_kernel(const QratioParams p) {
 
             if (!LEVELS) {
                 // ---- one level per item: score and emit pair by pair ------------------------
-                for (uint32_t li = 0; li < nl; ++li) {
-                    const uint32_t lg0 = s_item_g0[li], kl = s_item_g0[li + 1] - lg0;
+                auto emit_flat = [&](uint32_t li, uint32_t kl, uint32_t n, uint32_t lcs) {
                     bool ok = r_valid && keep_categories(p.job.cat_mode, s_cat[li], rcat);
                     double score = 0.0;
-                    if (kl) {  // uniform; threads without a right level compute on stale masks, unused
-                        const uint32_t n = s_lev_len[lg0];
-                        const uint32_t lcs = lcs_bitparallel<W>(pm, nthr, s_chr + s_lev_off[lg0], n);
-                        if (kr) {
-                            // flat: score_func(l0, r0); else compare_terms on K = 1 items: t = 1, weight 1/2
-                            score = qratio_from_lcs(m, n, lcs);
-                            if (!flat) score = __fma_rn(score, 0.5, 0.0);
-                            ++st_evals;
-                        }
+                    if (kl && kr) {
+                        // flat: score_func(l0, r0); else compare_terms on K = 1 items: t = 1, weight 1/2
+                        score = qratio_from_lcs(m, n, lcs);
+                        if (!flat) score = __fma_rn(score, 0.5, 0.0);
+                        ++st_evals;
                     }
                     if (ok && (kl == 0) != (kr == 0)) {  // IndexError in the reference
                         atomicOr(p.job.out_flags, NSM_FLAG_EMPTY_ITEM);
@@ -232,6 +363,27 @@ qratio_allpairs_kernel(const QratioParams p) {
                     }
                     emit_pairs(ok && score >= thr, l0 + li, r, score, p.job.out_pairs,
                                p.job.out_capacity, count, p.job.out_flags);
+                };
+                // (uniform control flow; threads without a right level compute on stale masks, unused)
+                for (uint32_t li = 0; li < nl;) {
+                    const uint32_t lg0 = s_item_g0[li], kl = s_item_g0[li + 1] - lg0;
+                    const uint32_t n = kl ? s_lev_len[lg0] : 0u;
+                    if (Q_DUAL && W <= 4 && li + 1 < nl) {
+                        const uint32_t lg1 = s_item_g0[li + 1], kl1 = s_item_g0[li + 2] - lg1;
+                        if (kl && kl1) {
+                            const uint32_t n1 = s_lev_len[lg1];
+                            uint32_t lcs0, lcs1;
+                            lcs_bitparallel2<W>(pm, nthr, s_chr + s_lev_off[lg0], n, s_chr + s_lev_off[lg1], n1,
+                                                lcs0, lcs1);
+                            emit_flat(li, kl, n, lcs0);
+                            emit_flat(li + 1, kl1, n1, lcs1);
+                            li += 2;
+                            continue;
+                        }
+                    }
+                    const uint32_t lcs = kl ? lcs_bitparallel<W>(pm, nthr, s_chr + s_lev_off[lg0], n) : 0u;
+                    emit_flat(li, kl, n, lcs);
+                    ++li;
                 }
             } else {
                 // ---- compare_terms' schedule as the outer loop, partial scores in smem --------
@@ -247,16 +399,47 @@ qratio_allpairs_kernel(const QratioParams p) {
                         const uint32_t slot = min(t, kr - 1);
                         if (slot != cur_slot) { cur_slot = slot; m = build_masks(rg0 + slot); }
                     }
-                    for (uint32_t li = 0; li < nl; ++li) {
-                        const uint32_t lg0 = s_item_g0[li], kl = s_item_g0[li + 1] - lg0;
-                        if (kl == 0 || t > max(kl, max_kr)) continue;  // uniform: nobody needs this step
-                        const uint32_t gl = lg0 + min(t, kl - 1);
-                        const uint32_t n = s_lev_len[gl];
-                        const uint32_t lcs = lcs_bitparallel<W>(pm, nthr, s_chr + s_lev_off[gl], n);
+                    // the tile's items that take part in step t (uniform), two per round
+                    auto level_of = [&](uint32_t li, uint32_t &kl) {
+                        const uint32_t lg0 = s_item_g0[li];
+                        kl = s_item_g0[li + 1] - lg0;
+                        return lg0 + min(t, max(kl, 1u) - 1);
+                    };
+                    auto takes_part = [&](uint32_t li) {
+                        const uint32_t kl = s_item_g0[li + 1] - s_item_g0[li];
+                        return kl != 0 && t <= max(kl, max_kr);
+                    };
+                    auto add_score = [&](uint32_t li, uint32_t kl, uint32_t n, uint32_t lcs) {
                         if (r_valid && kr && t <= max(kl, kr)) {
                             double *a = s_acc + (size_t)li * nthr + tid;
                             *a = __fma_rn(qratio_from_lcs(m, n, lcs), w, *a);
                             ++st_evals;
+                        }
+                    };
+                    uint32_t li = 0;
+                    while (true) {
+                        while (li < nl && !takes_part(li)) ++li;
+                        if (li >= nl) break;
+                        uint32_t kl0, kl1 = 0;
+                        const uint32_t g0 = level_of(li, kl0), n0 = s_lev_len[g0];
+                        uint32_t lj = li + 1;
+                        if (Q_DUAL && W <= 4) {
+                            while (lj < nl && !takes_part(lj)) ++lj;
+                        } else {
+                            lj = nl;
+                        }
+                        if (lj < nl) {
+                            const uint32_t g1 = level_of(lj, kl1), n1 = s_lev_len[g1];
+                            uint32_t lcs0, lcs1;
+                            lcs_bitparallel2<W>(pm, nthr, s_chr + s_lev_off[g0], n0, s_chr + s_lev_off[g1], n1,
+                                                lcs0, lcs1);
+                            add_score(li, kl0, n0, lcs0);
+                            add_score(lj, kl1, n1, lcs1);
+                            li = lj + 1;
+                        } else {
+                            const uint32_t lcs = lcs_bitparallel<W>(pm, nthr, s_chr + s_lev_off[g0], n0);
+                            add_score(li, kl0, n0, lcs);
+                            li = (Q_DUAL && W <= 4) ? nl : li + 1;
                         }
                     }
                 }
