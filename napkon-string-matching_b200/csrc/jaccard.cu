@@ -306,10 +306,9 @@ jaccard_allpairs_kernel(const JaccardParams p) {
         const uint32_t r = r0 + tid;
         const bool r_valid = r < p.R.n_items;
         uint32_t kr = 0;
-        uint64_t rcat = 0, rany_h = 0, rany_t = 0;
+        uint64_t rany_h = 0, rany_t = 0;
         if (r_valid) {
             kr = __ldg(p.R.item_k + r);
-            if (p.job.cat_mode) rcat = __ldg(p.job.r_cat + r);
             if (p.any_depth == 0) {
                 const ulonglong2 any = __ldg(reinterpret_cast<const ulonglong2 *>(p.R.item_any) + r);
                 rany_h = any.x; rany_t = any.y;
@@ -378,8 +377,6 @@ jaccard_allpairs_kernel(const JaccardParams p) {
                         pass[u] = r_valid && li_next + u < nl &&
                                   ((lany.x & rany_h) | (lany.y & rany_t)) != 0;
                     }
-                    if (p.job.cat_mode)
-                        pass[u] = pass[u] && keep_categories(p.job.cat_mode, __ldg(p.job.l_cat + l0 + li), rcat);
                     m[u] = __ballot_sync(FULL_MASK, pass[u]);
                 }
 #pragma unroll
@@ -418,8 +415,13 @@ jaccard_allpairs_kernel(const JaccardParams p) {
                 const uint32_t li = entry >> 5, rc = (warp << 5) | (entry & 31u);
                 const uint32_t kl = s.l_k[li], c_kr = s.r_k[rc];
                 bool pass = active;
+                // the category predicate runs here, once per round of survivors, not per pair of
+                // stage A (it is off in the shipped configuration)
+                if (p.job.cat_mode)
+                    pass = pass && keep_categories(p.job.cat_mode, __ldg(p.job.l_cat + l0 + li),
+                                                   __ldg(p.job.r_cat + min(r0 + rc, p.R.n_items - 1)));
                 float ub = 0.0f;
-                if (active && !pass_all && kl != 0 && c_kr != 0) {
+                if (pass && !pass_all && kl != 0 && c_kr != 0) {
                     const uint32_t kmax = flat ? 1u : max(kl, c_kr);
                     ++st_bound;
 #pragma unroll

@@ -252,11 +252,34 @@ __device__ __forceinline__ void lcs_bitparallel2(const uint64_t *__restrict__ pm
 #define Q_DUAL 1   // score two left strings per round where the registers allow it (W <= 4)
 #endif
 
+// Reciprocals of the possible length sums (two strings of up to 64 * Q_MAX_WORDS characters).
+struct LenRcpTable {
+    double v[64 * Q_MAX_WORDS * 2 + 1];
+    constexpr LenRcpTable() : v() {
+        for (int u = 1; u <= 64 * Q_MAX_WORDS * 2; ++u) v[u] = 1.0 / (double)u;
+    }
+};
+__device__ const LenRcpTable g_len_rcp = LenRcpTable();
+
+// a / b as  q0 = RN(a * r);  q = fma(fma(-q0, b, a), r, q0)  with r = RN(1 / b).  For the operands
+// qratio_from_lcs feeds it this equals the correctly rounded quotient - every case is enumerated
+// by tests/csrc/fast_ratio_check.c - and it costs three float64 operations instead of the general
+// division sequence.
+__device__ __forceinline__ double div_by_rcp(double a, double b, double r) {
+    const double q0 = __dmul_rn(a, r);
+    return __fma_rn(__fma_rn(-q0, b, a), r, q0);
+}
+
 // QRatio(a, b) / 100 from the counts: 0 when either processed string is empty, else
 // ((1.0 - dist / lensum) * 100) / 100 with dist = lensum - 2 LCS — this exact operation order.
 __device__ __forceinline__ double qratio_from_lcs(uint32_t m, uint32_t n, uint32_t lcs) {
     if (m == 0 || n == 0) return 0.0;
     const uint32_t lensum = m + n, dist = lensum - 2u * lcs;
+    if (lensum <= 64u * Q_MAX_WORDS * 2u) {
+        const double norm_dist = div_by_rcp((double)dist, (double)lensum, g_len_rcp.v[lensum]);
+        const double norm_sim = __dsub_rn(1.0, norm_dist);
+        return div_by_rcp(__dmul_rn(norm_sim, 100.0), 100.0, 0.01);  // 0.01 is RN(1 / 100)
+    }
     const double norm_dist = __ddiv_rn((double)dist, (double)lensum);
     const double norm_sim = __dsub_rn(1.0, norm_dist);
     return __ddiv_rn(__dmul_rn(norm_sim, 100.0), 100.0);

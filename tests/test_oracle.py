@@ -218,3 +218,19 @@ def test_reciprocal_fma_division_equals_true_division_for_small_counts():
             e = float(Fraction(a) - Fraction(q0) * Fraction(b))
             q = float(Fraction(q0) + Fraction(e) * Fraction(r))
             assert q == a / b, (i, u)
+
+
+def test_fast_ratio_arithmetic_is_exhaustively_exact(tmp_path):
+    """tests/csrc/fast_ratio_check.c enumerates every (dist, lensum) the fuzzy kernel's
+    division-free QRatio arithmetic can see (and every count pair of the Jaccard kernel's) and
+    compares reciprocal + two FMAs with the IEEE division bit for bit."""
+    import subprocess
+
+    from conftest import ROOT
+
+    exe = tmp_path / "fast_ratio_check"
+    subprocess.run(["gcc", "-O1", "-ffp-contract=off", "-o", str(exe),
+                    str(ROOT / "tests" / "csrc" / "fast_ratio_check.c"), "-lm"], check=True)
+    n, bad_div, bad_ratio = map(int, subprocess.run([str(exe), "1026"], check=True, capture_output=True,
+                                                    text=True).stdout.split())
+    assert n > 500_000 and bad_div == 0 and bad_ratio == 0
