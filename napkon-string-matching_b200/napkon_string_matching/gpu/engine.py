@@ -56,6 +56,7 @@ class Job:
 
 class Engine:
     PIPELINE_BLOCK_BYTES = 512 << 20
+    PIPELINE_MIN_PAIRS = 1 << 30   # smaller jobs are one launch: splitting them costs more than it hides
 
     def __init__(self, device: Optional[int] = None, max_pairs_per_block: int = 1 << 30):
         _require_cuda()
@@ -208,7 +209,8 @@ class Engine:
                           "item_pairs": max(0, end - begin) * job.right.n_items, "parts": []})
             if end > begin and job.right.n_items:
                 rows = end - begin
-                if to_host and self.pipeline_d2h and rows >= 8 * 1024 and capacity is None:
+                if (to_host and self.pipeline_d2h and capacity is None and rows >= 8 * 1024
+                        and rows * job.right.n_items >= self.PIPELINE_MIN_PAIRS):
                     cut = begin + rows // 8
                     probes.add((j, begin, cut))
                     work += [(j, begin, cut), (j, cut, end)]

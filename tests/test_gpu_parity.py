@@ -382,7 +382,8 @@ def test_pipelined_row_blocks_give_the_same_records(engine):
     pr = pack.pack_suffix_id_sets(lens, flat, 30000)
     dl, dr = engine.upload(pl), engine.upload(pr)
     key = lambda a: a[np.lexsort((a["right"], a["left"]))]
-    old = engine.pipeline_d2h, engine.PIPELINE_BLOCK_BYTES
+    old = engine.pipeline_d2h, engine.PIPELINE_BLOCK_BYTES, engine.PIPELINE_MIN_PAIRS
+    engine.PIPELINE_MIN_PAIRS = 1
     try:
         for thr in (0.1, 0.7):
             engine.pipeline_d2h = False
@@ -399,4 +400,4 @@ def test_pipelined_row_blocks_give_the_same_records(engine):
             part = key(engine.all_pairs(dl, dr, thr, rows=(1000, 19000)))
             assert np.array_equal(part, want[(want["left"] >= 1000) & (want["left"] < 19000)])
     finally:
-        engine.pipeline_d2h, engine.PIPELINE_BLOCK_BYTES = old
+        engine.pipeline_d2h, engine.PIPELINE_BLOCK_BYTES, engine.PIPELINE_MIN_PAIRS = old
