@@ -558,6 +558,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         sec_step_hbm = kernel_sec_step
         if args.quick:   # kernel experiments: no CPU baseline leg (not a bench line to report)
             cpu_val, cpu_sample = None, "skipped (--quick)"
+        elif world > 1:  # the CPU baseline is timed at N = 1 only
+            cpu_val, cpu_sample = None, "timed at N=1 only"
         else:
             cpu_val, cpu_sample = cpu_reference(wl, raw, pairs, 12.0, 1, packs)
         line = {
