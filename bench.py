@@ -415,7 +415,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     from napkon_string_matching.gpu.engine import Engine
 
     torch.cuda.set_device(local_rank)
+    bound_cpus = None
     if world > 1:
+        # one rank per GPU: keep the rank (and so its pinned record arena) on the GPU's NUMA node
+        from napkon_string_matching.gpu import affinity
+
+        bound_cpus = affinity.bind_to_gpu(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     wl = WORKLOADS[args.workload]
     packs, raw, pairs = build_workload(wl, rank)
@@ -595,6 +600,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                     "d2h_bytes_per_step": d2h, "from": e2e_from},
             "pack": pack_info,
             "gpu_launches": launches,
+            "numa": {"rank0_bound_to_cpus": len(bound_cpus) if bound_cpus else None},
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

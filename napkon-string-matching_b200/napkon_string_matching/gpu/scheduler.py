@@ -68,6 +68,11 @@ def _run_threads(tasks: List[ComparisonTask], engines: List[Any]) -> List[Any]:
 
     def worker(k: int):
         try:
+            device = getattr(engines[k], "device", None)
+            if device is not None and len(engines) > 1:   # this thread's pinned arenas: local node
+                from napkon_string_matching.gpu import affinity
+
+                affinity.bind_to_gpu(device.index)
             with engine_mod.use_engine(engines[k]):
                 for i in assignment[k]:
                     results[i] = tasks[i].run()

@@ -96,3 +96,20 @@ def test_scheduler_threads_on_the_gpu(engine, tmp_path):
     assert list(a) == list(b)
     for name in a:
         assert a[name].equals(b[name]), name
+
+
+def test_affinity_binds_to_gpu_local_cpus_or_leaves_everything_alone():
+    import os
+
+    from napkon_string_matching.gpu import affinity
+
+    before = os.sched_getaffinity(0)
+    try:
+        got = affinity.bind_to_gpu(0)
+        now = os.sched_getaffinity(0)
+        if got is None:
+            assert now == before
+        else:
+            assert set(got) == now and now < before and now <= set(affinity.gpu_local_cpus(0))
+    finally:
+        os.sched_setaffinity(0, before)

@@ -136,3 +136,15 @@ def test_rank_mode_world_size_2_gloo(tmp_path):
         capture_output=True, text=True, timeout=300, env={**os.environ, "OMP_NUM_THREADS": "2"})
     assert res.returncode == 0, res.stdout + res.stderr
     assert res.stdout.count("ok") == 2, res.stdout
+
+
+def test_affinity_is_best_effort_without_a_gpu():
+    """gpu/affinity.py never raises: without NVML / a GPU it reports None and changes nothing."""
+    import torch
+
+    from napkon_string_matching.gpu import affinity
+
+    before = os.sched_getaffinity(0)
+    if not torch.cuda.is_available():
+        assert affinity.gpu_local_cpus(0) is None and affinity.bind_to_gpu(0) is None
+    assert os.sched_getaffinity(0) == before or torch.cuda.is_available()
