@@ -39,7 +39,9 @@ sys.path.insert(0, str(ROOT))
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the
 # committed `ncu --set full` captures (profiles/r1_v9_jaccard_tokenids50k.txt,
 # profiles/r1_v9_jaccard_term200k.txt, profiles/r1_qratio_v2_fuzzy20k.txt); other workloads: null
-NCU_DRAM_BYTES_PER_LAUNCH = {"tokenids50k": 2.2035e9, "term200k": 4.06e7, "fuzzy20k": 2.3e6}
+# dram__bytes_read.sum + dram__bytes_write.sum per kernel launch, from the committed ncu --set full
+# captures (profiles/r1_v13_*.txt)
+NCU_DRAM_BYTES_PER_LAUNCH = {"tokenids50k": 2.1932e9, "term200k": 4.45e7, "fuzzy20k": 2.3e6}
 
 METRIC = "item pair-scores/sec (scored+thresholded)"
 UNIT = "pair-scores/s"

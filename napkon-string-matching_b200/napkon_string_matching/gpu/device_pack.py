@@ -20,7 +20,8 @@ import torch
 
 from napkon_string_matching.gpu import lib as nsmlib
 from napkon_string_matching.gpu.engine import DeviceCohort, Engine
-from napkon_string_matching.gpu.pack import (HEAD_IDS, SLOT_BLOCK, SLOT_CAP, PackedSets, PackError)
+from napkon_string_matching.gpu.pack import (HEAD_IDS, SLOT_BLOCK, SLOT_CAP, PackedSets, PackError,
+                                             PackTooLarge)
 
 
 @dataclass
@@ -207,8 +208,8 @@ class DevicePacker:
         if flags & nsmlib.PACK_FLAG_BAD_ID:
             raise PackError("a token code is >= n_vocab")
         if flags & nsmlib.PACK_FLAG_TOO_LARGE:
-            raise PackError(f"an item holds more than {nsmlib.PACK_MAX_ITEM_IDS} ids (or 65535 levels); "
-                            "pack this cohort with gpu.pack on the host")
+            raise PackTooLarge(f"an item holds more than {nsmlib.PACK_MAX_ITEM_IDS} ids (or 65535 levels); "
+                               "pack this cohort with gpu.pack on the host")
 
 
 _DTYPES = {"item_level_off": np.uint32, "level_tok_off": np.uint32, "tok": np.uint32,

@@ -66,6 +66,10 @@ class PackError(ValueError):
     pass
 
 
+class PackTooLarge(PackError):
+    """An item exceeds what the device packer holds per item; the numpy packer has no such limit."""
+
+
 @dataclass
 class PackedSets:
     item_level_off: np.ndarray

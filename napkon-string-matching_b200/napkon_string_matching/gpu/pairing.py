@@ -162,8 +162,8 @@ def upload_levels(engine, left_levels, right_levels, score_func: str):
         try:
             dl, dr = packer.pack(raws, len(uniques), rank="frequency")
             return dl, dr, (None, None)
-        except pack.PackError:
-            pass
+        except pack.PackTooLarge:
+            pass   # the numpy packer below has no per-item limit
     pl, pr = pack_levels(left_levels, right_levels, score_func)
     return engine.upload(pl), engine.upload(pr), (getattr(pl, "perm", None), getattr(pr, "perm", None))
 

@@ -154,3 +154,21 @@ def test_full_size_term_pack(engine):
     rank = pack.frequency_rank([f], 20000)
     (cohort,) = engine.device_packer.pack([dp.raw_from_parts(pl, f)], 20000)
     assert_same_pack(cohort, pack.pack_part_id_sets(pl, f, 20000, rank))
+
+
+def test_oversized_items_fall_back_to_the_numpy_packer(engine):
+    """An item beyond the device packer's 1024 ids per item sends the comparison through the
+    numpy packer (pairing.upload_levels); the result is the oracle's either way."""
+    from napkon_string_matching.gpu import pairing
+
+    rng = np.random.default_rng(5)
+    big = [[f"w{int(x)}" for x in rng.integers(0, 5000, size=1500)]]          # one level, 1500 ids
+    L = [big] + [[[f"w{int(x)}" for x in rng.integers(0, 5000, size=6)]] for _ in range(40)]
+    R = [[[f"w{int(x)}" for x in rng.integers(0, 5000, size=700)]] for _ in range(30)]
+    dl, dr, _ = pairing.upload_levels(engine, L, R, "intersection_vs_union")
+    assert dl.sizes is None                       # numpy-packed
+    out = engine.all_pairs(dl, dr, 0.0)
+    pl, pr = pack.pack_sets(L, R)
+    want, _ = c_oracle.all_pairs(pl, pr, 0.0)
+    assert_same_triples((out["left"], out["right"], out["score"]),
+                        (want["left"], want["right"], want["score"]))
