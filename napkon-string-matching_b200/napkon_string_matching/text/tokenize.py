@@ -127,21 +127,36 @@ def _treebank(sentence: str) -> List[str]:
     for rx in _CONTRACT2:
         text = rx.sub(r" \1 \2 ", text)
     for rx in _CONTRACT3:
-        text = rx.sub(r" \1 \2 \3 ", text)
+        text = rx.sub(r" \1 \2 ", text)
     return text.split()
 
 
 _SIMPLE = re.compile(r"^[\w \t\n\r\-/+]*$")  # nothing any rule above would touch
 
 
+_nltk_word_tokenize = None   # nltk's tokeniser once resolved; False when nltk cannot be used
+
+
+def _resolve_nltk():
+    """Looks for nltk ONCE (a failing import costs half a millisecond, per call it was three
+    quarters of the host time of a comparison) and checks that its punkt data is usable."""
+    global _nltk_word_tokenize
+    if _nltk_word_tokenize is None:
+        try:
+            from nltk.tokenize import word_tokenize as fn  # type: ignore
+
+            fn("Probe. Satz?")
+            _nltk_word_tokenize = fn
+        except Exception:  # noqa: BLE001 - not installed, or its data files are missing
+            _nltk_word_tokenize = False
+    return _nltk_word_tokenize
+
+
 def word_tokenize(text: str) -> List[str]:
     """``nltk.word_tokenize(text)`` (default language), or its restatement."""
-    try:
-        from nltk.tokenize import word_tokenize as _nltk_word_tokenize  # type: ignore
-
-        return _nltk_word_tokenize(text)
-    except Exception:
-        pass
+    fn = _resolve_nltk()
+    if fn:
+        return fn(text)
     if _SIMPLE.match(text) and "--" not in text:
         return text.split()
     out: List[str] = []
@@ -174,5 +189,30 @@ def tokenize(parts, language: str = "german") -> List[str]:
 
 
 def gen_comp_value(items) -> List[List[str]]:
-    """Level j = token set of the last j+1 parts (comparable_data.py:283-285)."""
+    """Level j = token set of the last j+1 parts (comparable_data.py:283-285).
+
+    The reference tokenises every suffix from scratch (K (K + 1) / 2 part tokenisations per item).
+    When the restated tokeniser is in use and no string of the item contains anything its rules
+    would touch, the words of a suffix are just the words of its parts, so the levels are built
+    incrementally: each part is split and filtered once, level j is level j-1 plus one part."""
+    if _resolve_nltk() is False:
+        fast = _gen_comp_value_simple(items)
+        if fast is not None:
+            return fast
     return [tokenize(items[-i:]) for i in range(1, len(items) + 1)]
+
+
+def _gen_comp_value_simple(items):
+    stops = stop_words("german")
+    kept: set = set()                                  # (casefold, word): sorts without a key call
+    levels = []
+    for part in reversed(items):                       # the part that enters at the next level
+        for text in (part if isinstance(part, list) else (part,)):
+            if not isinstance(text, str) or "--" in text or not _SIMPLE.match(text):
+                return None
+            for w in text.split():
+                folded = w.casefold()
+                if folded not in stops and w not in PREPARE_REMOVE_SYMBOLS:
+                    kept.add((folded, w))
+        levels.append([w for _, w in sorted(kept)])
+    return levels

@@ -105,6 +105,11 @@ class Comparable:
         self.data.drop_superfluous_columns(columns)
 
     def to_json(self, orient: str | None = None, *args, **kwargs) -> str:
+        if orient == "records" and not args and set(kwargs) == {"indent"} and isinstance(kwargs["indent"], int):
+            fast = _records_payload_json(self.left_name, self.right_name, self.data.dataframe(),
+                                         kwargs["indent"])
+            if fast is not None:
+                return fast
         payload = {LEFT_NAME: self.left_name, RIGHT_NAME: self.right_name,
                    DATA_NAME: self.data.to_dict(orient=orient)}
         return json.dumps(payload, *args, **kwargs)
@@ -115,6 +120,43 @@ class Comparable:
 
     def write_json(self, file_name: str | Path, *args, **kwargs) -> None:
         Path(file_name).write_text(self.to_json(orient="records", indent=4), encoding="utf-8")
+
+
+def _records_payload_json(left_name, right_name, frame: pd.DataFrame, indent: int) -> str | None:
+    """The text ``json.dumps({left_name, right_name, data: frame.to_dict("records")}, indent=n)``
+    produces (the reference's cache file, comparable.py:61-67 + writable_json.py:20), built column
+    by column: every column is encoded by ONE call of the C encoder (an indented ``json.dumps``
+    runs the pure-Python encoder: 18 s for 200k kept pairs) and the lines are assembled with
+    string joins.  Returns None for frames it does not cover (nested cells, no columns, indent
+    <= 0); the caller then takes the generic path."""
+    if indent <= 0 or frame.shape[1] == 0 or not all(isinstance(c, str) for c in frame.columns):
+        return None
+    pad1, pad2, pad3 = " " * indent, " " * (2 * indent), " " * (3 * indent)
+    head = ("{\n" + pad1 + json.dumps(LEFT_NAME) + ": " + json.dumps(left_name) + ",\n"
+            + pad1 + json.dumps(RIGHT_NAME) + ": " + json.dumps(right_name) + ",\n"
+            + pad1 + json.dumps(DATA_NAME) + ": ")
+    n = len(frame)
+    if n == 0:
+        return head + "[]\n}"
+    columns = []
+    last = frame.shape[1] - 1
+    for j, name in enumerate(frame.columns):
+        values = frame[name].tolist()
+        try:
+            # "\x00" cannot occur inside an encoded value (control characters are escaped)
+            text = json.dumps(values, separators=("\x00", ": "))[1:-1]
+        except (TypeError, ValueError):
+            return None
+        if text[:1] in "[{" or "\x00[" in text or "\x00{" in text:
+            return None  # a list / dict cell: its inner layout depends on the indent
+        encoded = text.split("\x00")
+        if len(encoded) != n:
+            return None
+        prefix = (pad2 + "{\n" if j == 0 else "") + pad3 + json.dumps(name) + ": "
+        suffix = ",\n" if j < last else "\n" + pad2 + "}"
+        columns.append([prefix + e + suffix for e in encoded])
+    records = map("".join, zip(*columns))
+    return head + "[\n" + ",\n".join(records) + "\n" + pad1 + "]\n}"
 
 
 class ComparisonResults:

@@ -198,6 +198,8 @@ class ComparableData(Data):
 
     @classmethod
     def gen_comp_value(cls, items: List[str]) -> List[str]:
+        if cls.tokenize is ComparableData.tokenize:   # not overridden: the incremental builder
+            return _tok.gen_comp_value(items)
         return [cls.tokenize(items[-i:]) for i in range(1, len(items) + 1)]
 
     @staticmethod

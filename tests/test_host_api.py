@@ -222,3 +222,44 @@ def test_terminology_get_matches_host_logic(oracle_engine):
 
     terminology_cases.check_all()
     terminology_cases.check_add_tokens()
+
+
+def test_cache_json_fast_writer_is_byte_identical_to_json_dumps():
+    """Comparable.to_json(orient="records", indent=4) — the reference's cache file format — is
+    assembled column-wise with the C encoder; the text must equal the generic indented dump."""
+    import json
+
+    import pandas as pd
+
+    from napkon_string_matching.types.comparable import Comparable
+
+    def generic(c, indent):
+        payload = {"left_name": c.left_name, "right_name": c.right_name,
+                   "data": c.data.to_dict(orient="records")}
+        return json.dumps(payload, indent=indent)
+
+    rng = np.random.default_rng(0)
+    nasty = ['plain', 'quote " and \\\\ backslash', 'umlaut äöüß €', 'tab\\tnewline\\n', 'nul \\x00 ctl \\x1f',
+             '', '", "', '[not a list]', '{"not": "a dict"}', 'emoji \\U0001F600']
+    frame = pd.DataFrame({
+        "HapIdentifier": [nasty[i % len(nasty)] for i in range(57)],
+        "HapVariable": [None if i % 7 == 0 else f"v{i}" for i in range(57)],
+        "PopSheet": [float("nan") if i % 5 == 0 else f"s{i}" for i in range(57)],
+        "Count": rng.integers(-5, 5, size=57),
+        "Flag": rng.random(57) < 0.5,
+        "MatchScore": np.where(rng.random(57) < 0.1, np.nan, rng.random(57)),
+    })
+    for indent in (4, 1, 2):
+        for fr in (frame, frame.iloc[:1], frame.iloc[:0]):
+            c = Comparable(data=fr, left_name="Hap", right_name='P"op')
+            assert c.to_json(orient="records", indent=indent) == generic(c, indent)
+    # cells that are lists go through the generic path and still round-trip
+    c = Comparable(data=pd.DataFrame({"A": [[1, 2], [3]], "MatchScore": [0.5, 0.25]}), left_name="L", right_name="R")
+    assert c.to_json(orient="records", indent=4) == generic(c, 4)
+    # read_json(write_json(x)) == x
+    c = Comparable(data=frame[["HapIdentifier", "MatchScore"]].dropna(), left_name="Hap", right_name="Pop")
+    import tempfile, pathlib
+    with tempfile.TemporaryDirectory() as d:
+        c.write_json(pathlib.Path(d) / "c.json")
+        back = Comparable.read_json(pathlib.Path(d) / "c.json")
+    assert back.dataframe().reset_index(drop=True).equals(c.dataframe().reset_index(drop=True))
