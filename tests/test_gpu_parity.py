@@ -401,3 +401,85 @@ def test_pipelined_row_blocks_give_the_same_records(engine):
             assert np.array_equal(part, want[(want["left"] >= 1000) & (want["left"] < 19000)])
     finally:
         engine.pipeline_d2h, engine.PIPELINE_BLOCK_BYTES, engine.PIPELINE_MIN_PAIRS = old
+
+
+def _keyed(rec, n_right):
+    key = rec["left"].astype(np.uint64) * np.uint64(n_right) + rec["right"]
+    order = np.argsort(key, kind="stable")
+    return key[order], rec["score"][order]
+
+
+def check_term_threshold_regimes(engine, n_items, block):
+    """cfg5 shape (Term items, K 2-4) at thr 0.5: stage A asks for TWO shared signature bits.
+    Properties that do not depend on size: the kept set is the part of the thr-0.45 result (where
+    nearly every item is "wild" and stage A falls back to one shared bit) with score >= 0.5; every
+    kept score is the oracle's; on a sub-block the oracle's full enumeration finds the same pairs."""
+    L = syn.term_level_sets(n_items, syn.SEED_LEFT)
+    R = syn.term_level_sets(n_items, syn.SEED_RIGHT)
+    rank = pack.frequency_rank([L[1], R[1]], 20000)
+    pl, pr = pack.pack_part_id_sets(*L, 20000, rank), pack.pack_part_id_sets(*R, 20000, rank)
+    dl, dr = engine.upload(pl), engine.upload(pr)
+    hi = engine.all_pairs(dl, dr, 0.5)
+    assert engine.last_info["stats"]["bound_pairs"] < 0.55 * n_items * n_items   # the TWO filter is on
+    lo = engine.all_pairs(dl, dr, 0.45)
+    n_bound_lo = engine.last_info["stats"]["bound_pairs"]
+    assert n_bound_lo > 0.6 * n_items * n_items                                    # one-bit regime
+    khi, shi = _keyed(hi, pr.n_items)
+    klo, slo = _keyed(lo, pr.n_items)
+    assert len(khi) == len(np.unique(khi)) and len(klo) == len(np.unique(klo))
+    sel = slo >= 0.5
+    assert np.array_equal(klo[sel], khi)
+    assert np.array_equal(slo[sel].view(np.uint64), shi.view(np.uint64))
+    want, _ = c_oracle.score_pairs(pl, pr, lo["left"], lo["right"])
+    assert np.array_equal(want.view(np.uint64), lo["score"].view(np.uint64))
+    # full enumeration of a sub-block by the oracle
+    b0, b1 = block
+    sub, _ = c_oracle.all_pairs(pl, pr.rows(0, b1 - b0), 0.45, l_begin=b0, l_end=b1)
+    in_block = (lo["left"] >= b0) & (lo["left"] < b1) & (lo["right"] < b1 - b0)
+    assert_same_triples((lo["left"][in_block], lo["right"][in_block], lo["score"][in_block]),
+                        (sub["left"], sub["right"], sub["score"]))
+    return len(hi), len(lo)
+
+
+def test_term_full_size_threshold_regimes(engine):
+    n_hi, n_lo = check_term_threshold_regimes(engine, 200_000, (150_000, 156_000))
+    assert 0 < n_hi < n_lo
+
+
+def check_fuzzy_flat_properties(engine, n_items, thr=0.7):
+    """cfg3 shape (flat fuzzy_match on ~60-character strings): kept scores equal the oracle's on a
+    sample, a sample of pairs that were not kept is below the threshold, swapping the sides keeps
+    the transposed set with the same scores."""
+    from napkon_string_matching.text.process import default_process
+
+    vocab = syn.vocabulary()
+    sl = [[default_process(s)] for s in syn.question_strings(n_items, syn.SEED_LEFT, vocab)]
+    sr = [[default_process(s)] for s in syn.question_strings(n_items + 77, syn.SEED_RIGHT, vocab)]
+    pl, pr = pack.pack_strings(sl, sr)
+    dl, dr = engine.upload(pl), engine.upload(pr)
+    rec = engine.all_pairs(dl, dr, thr, flat=True)
+    assert engine.last_info["count"] == len(rec) > 0
+    key, score = _keyed(rec, len(sr))
+    assert len(np.unique(key)) == len(key)
+    swapped = engine.all_pairs(dr, dl, thr, flat=True)
+    skey = swapped["right"].astype(np.uint64) * np.uint64(len(sr)) + swapped["left"]
+    sorder = np.argsort(skey, kind="stable")
+    assert np.array_equal(skey[sorder], key)
+    assert np.array_equal(swapped["score"][sorder].view(np.uint64), score.view(np.uint64))
+    # records and c_oracle.score_pairs both speak the caller's item indices
+    rng = np.random.default_rng(3)
+    pick = rng.choice(len(rec), size=min(len(rec), 20_000), replace=False)
+    want, _ = c_oracle.score_pairs(pl, pr, rec["left"][pick], rec["right"][pick], flat=True)
+    assert np.array_equal(want.view(np.uint64), rec["score"][pick].view(np.uint64))
+    li = rng.integers(0, len(sl), size=100_000).astype(np.uint32)
+    ri = rng.integers(0, len(sr), size=100_000).astype(np.uint32)
+    probe = li.astype(np.uint64) * np.uint64(len(sr)) + ri
+    pos = np.searchsorted(key, probe)
+    kept = (pos < len(key)) & (key[np.minimum(pos, len(key) - 1)] == probe)
+    got, _ = c_oracle.score_pairs(pl, pr, li, ri, flat=True)
+    assert np.array_equal(got >= thr, kept)
+    return len(rec)
+
+
+def test_fuzzy_flat_20k_properties(engine):
+    assert check_fuzzy_flat_properties(engine, 20_000) > 50_000
