@@ -96,14 +96,21 @@ def _run_ranks(tasks: List[ComparisonTask]) -> List[Any]:
 
     rank, world = dist.get_rank(), dist.get_world_size()
     assignment = plan([t.work for t in tasks], world)
-    mine = {}
+    mine: Dict[int, Any] = {}
+    failure: Optional[BaseException] = None
     with distributed.whole_comparisons():
-        for i in assignment[rank]:
-            mine[i] = tasks[i].run()
-    everyone: List[Optional[dict]] = [None] * world
-    dist.all_gather_object(everyone, mine, group=distributed.host_group())
-    merged = {}
-    for part in everyone:
+        try:
+            for i in assignment[rank]:
+                mine[i] = tasks[i].run()
+        except Exception as exc:  # noqa: BLE001 - must still reach the exchange: the others wait there
+            failure = exc
+    everyone: List[Optional[tuple]] = [None] * world
+    dist.all_gather_object(everyone, (mine, failure), group=distributed.host_group())
+    for r, (_, exc) in enumerate(everyone):
+        if exc is not None:   # every rank raises the first failure (lowest rank), like the
+            raise exc         # sequential loop would have raised it on its only process
+    merged: Dict[int, Any] = {}
+    for part, _ in everyone:
         merged.update(part)
     return [merged[i] for i in range(len(tasks))]
 

@@ -148,3 +148,41 @@ def test_affinity_is_best_effort_without_a_gpu():
     if not torch.cuda.is_available():
         assert affinity.gpu_local_cpus(0) is None and affinity.bind_to_gpu(0) is None
     assert os.sched_getaffinity(0) == before or torch.cuda.is_available()
+
+
+FAILING_RANK_WORKER = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, {pkg!r}); sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
+    import torch.distributed as dist
+    from napkon_string_matching.gpu import scheduler
+
+    class Item:
+        def __init__(self, n, boom=False):
+            self.n, self.boom = n, boom
+        def __len__(self):
+            return self.n
+        def compare(self, other, **kw):
+            if self.boom:
+                raise ZeroDivisionError("division by zero")
+            return self.n * len(other)
+
+    dist.init_process_group("gloo")
+    # task 1 (the second largest) lands on rank 1 and fails there; rank 0 must not hang in the exchange
+    tasks = [scheduler.ComparisonTask(f"t{{i}}", Item(n, boom=(i == 1)), Item(3)) for i, n in enumerate((9, 8, 2, 1))]
+    try:
+        scheduler.run_comparisons(tasks)
+    except ZeroDivisionError:
+        sys.stdout.write("rank%sraised" % dist.get_rank() + chr(10))
+    dist.destroy_process_group()
+""")
+
+
+def test_a_failing_rank_fails_every_rank_instead_of_hanging(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(FAILING_RANK_WORKER.format(pkg=str(PKG), root=str(ROOT), tests=str(ROOT / "tests")))
+    res = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+         "--master-addr", "127.0.0.1", "--master-port", "29583", str(script)],
+        capture_output=True, text=True, timeout=120, env={**os.environ, "OMP_NUM_THREADS": "2"})
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert res.stdout.count("raised") == 2, res.stdout + res.stderr
