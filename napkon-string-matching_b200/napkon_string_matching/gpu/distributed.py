@@ -96,8 +96,17 @@ def sharded_all_pairs(score_block: Callable[[int, int], np.ndarray], weights: np
         last_counts = [len(out)]
         return out
     begin, end = partition_rows(weights, world)[rank]
-    mine = score_block(begin, end) if end > begin else np.zeros(0, dtype=PAIR_DTYPE)
-    counts = allgather_counts(len(mine))
+    failure = None
+    try:
+        mine = score_block(begin, end) if end > begin else np.zeros(0, dtype=PAIR_DTYPE)
+    except Exception as exc:  # noqa: BLE001 - the other ranks wait in the collective below
+        failure, mine = exc, np.zeros(0, dtype=PAIR_DTYPE)
+    # a count of -1 tells every rank that a block failed, so that nobody is left in a gather
+    counts = allgather_counts(-1 if failure is not None else len(mine))
+    if failure is not None:
+        raise failure
+    if min(counts) < 0:
+        raise RuntimeError(f"scoring the row block of rank {counts.index(-1)} failed")
     last_counts = counts
     if not gather:
         return mine

@@ -201,6 +201,18 @@ GLOO_WORKER = textwrap.dedent("""
     assert np.array_equal(got[key(got)], want[key(want)])
     mine = distributed.sharded_all_pairs(score, weights, gather=False)
     assert len(mine) == distributed.last_counts[dist.get_rank()]
+    # a block that fails on one rank fails the call on every rank (nobody hangs in the gather)
+    def broken(b, e):
+        if dist.get_rank() == 1:
+            raise ZeroDivisionError("division by zero")
+        return score(b, e)
+    try:
+        distributed.sharded_all_pairs(broken, weights)
+        raise SystemExit("no exception")
+    except ZeroDivisionError:
+        assert dist.get_rank() == 1
+    except RuntimeError as exc:
+        assert dist.get_rank() == 0 and "rank 1" in str(exc)
     dist.destroy_process_group()
     sys.stdout.write("rank%sok" % os.environ["RANK"] + chr(10))
 """)
