@@ -483,3 +483,13 @@ def check_fuzzy_flat_properties(engine, n_items, thr=0.7):
 
 def test_fuzzy_flat_20k_properties(engine):
     assert check_fuzzy_flat_properties(engine, 20_000) > 50_000
+
+
+def test_jaccard_two_bit_filter_with_folded_shared_ids(engine):
+    """The crafted pair of tests/test_filter_soundness.py — its two shared step-1 ids fold onto
+    one signature bit — must come out of the kernel with the oracle's score at thr 0.5."""
+    import test_filter_soundness as fs
+
+    pl, pr = fs.folded_pair_packs()
+    out, info = check_against_oracle(engine, pl, pr, 0.5)
+    assert len(out) == 1 and info["flags"] == 0
