@@ -150,3 +150,42 @@ def test_two_bit_filter_keeps_a_pair_whose_shared_ids_fold_onto_one_signature_bi
     bits = popcount(hl & hr) + popcount(tl & tr)
     assert bits[0] == 1 and wl[0] and wr[0]      # one shared bit, and only the fold flag saves it
     assert (pl.slot_info[0, 0] >> 16) == 1 and (pl.slot_info[0, 0] & 0xFFFF) == 5 > two
+
+
+def stage_b_bound(pl, pr, unroll=6):
+    """Real-valued version of the kernel's stage B: upper bound of compare_terms' score of every
+    pair from the slot summaries (jaccard.cu:bound_intersection / bound_step; the kernel evaluates
+    the same expressions in fp32 with every operation rounded up)."""
+    nl, nr = pl.n_items, pr.n_items
+    kmax = np.maximum(pl.item_k[:, None].astype(np.int64), pr.item_k[None, :].astype(np.int64))
+    exact = pl.exact_bits and pr.exact_bits
+    ub = np.zeros((nl, nr))
+    for t in range(1, unroll + 1):
+        sl, sr = min(t, pl.n_slots) - 1, min(t, pr.n_slots) - 1
+        ha, ta, ia = pl.slot_ht[sl, :nl, 0], pl.slot_ht[sl, :nl, 1], pl.slot_info[sl, :nl].astype(np.int64)
+        hb, tb, ib = pr.slot_ht[sr, :nr, 0], pr.slot_ht[sr, :nr, 1], pr.slot_info[sr, :nr].astype(np.int64)
+        both = ta[:, None] & tb[None, :]
+        fold = np.minimum(ia[:, None] >> 16, ib[None, :] >> 16)
+        extra = np.where(fold == 255, 1 << 16, fold) if not exact else 0
+        it = np.where(both != 0, popcount(both) + extra, 0)
+        a, b = (ia & 0xFFFF)[:, None], (ib & 0xFFFF)[None, :]
+        ih = np.minimum(popcount(ha[:, None] & hb[None, :]) + it, np.minimum(a, b))
+        union = a + b - ih
+        ub += np.where(t <= kmax, np.where(union > 0, ih / np.maximum(union, 1), 0.0) * 2.0 ** -t, 0.0)
+    return ub + np.where(kmax > unroll, 2.0 ** -unroll - 2.0 ** -kmax.astype(float), 0.0)
+
+
+@pytest.mark.parametrize("vocab,max_k,per_part,zipf", [(70, 4, 5, 1.2), (400, 4, 9, 1.2), (3000, 3, 30, 1.3),
+                                                        (20000, 4, 6, 1.1), (500, 9, 2, 1.3)])
+def test_stage_b_bound_is_an_upper_bound_of_the_exact_score(vocab, max_k, per_part, zipf):
+    rng = np.random.default_rng(7 * vocab + max_k)
+    pl, pr = pack.pack_sets(suffix_items(rng, 220, max_k, per_part, vocab, zipf),
+                            suffix_items(rng, 260, max_k, per_part, vocab, zipf))
+    assert max(pl.max_levels, pr.max_levels) <= min(pl.n_slots, pr.n_slots) + 1   # slots hold every level
+    everything, _ = c_oracle.all_pairs(pl, pr, 0.0)
+    score = np.zeros((pl.n_items, pr.n_items))
+    score[everything["left"], everything["right"]] = everything["score"]
+    ub = stage_b_bound(pl, pr)
+    assert np.all(ub >= score - 1e-12), np.argwhere(ub < score - 1e-12)[:3]
+    # and it is a useful bound, not a trivial one: it separates most pairs from a threshold of 0.3
+    assert (ub < 0.3).mean() > 0.3
