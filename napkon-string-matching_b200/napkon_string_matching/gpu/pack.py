@@ -50,6 +50,7 @@ with the narrowest bit-vectors; ``perm`` maps a stored position back to the call
 from __future__ import annotations
 
 from dataclasses import dataclass
+from itertools import chain
 from typing import Iterable, List, Sequence, Tuple
 
 import numpy as np
@@ -335,18 +336,16 @@ def rank_by_frequency(codes_per_side: List[np.ndarray], n_vocab: int) -> List[np
 
 
 def _csr_from_nested(items_levels: Sequence[Sequence[Sequence]]) -> Tuple[np.ndarray, np.ndarray, list]:
-    k = np.fromiter((len(lv) for lv in items_levels), dtype=np.int64, count=len(items_levels))
+    k = np.fromiter(map(len, items_levels), dtype=np.int64, count=len(items_levels))
     item_level_off = np.zeros(len(k) + 1, dtype=np.int64)
     np.cumsum(k, out=item_level_off[1:])
-    sizes, flat = [], []
-    for lv in items_levels:
-        for level in lv:
-            if isinstance(level, str):  # intersection_vs_union splits a str operand
-                level = level.split()
-            sizes.append(len(level))
-            flat.extend(level)
+    levels = list(chain.from_iterable(items_levels))
+    if any(isinstance(level, str) for level in levels):  # intersection_vs_union splits a str operand
+        levels = [level.split() if isinstance(level, str) else level for level in levels]
+    sizes = np.fromiter(map(len, levels), dtype=np.int64, count=len(levels))
+    flat = list(chain.from_iterable(levels))
     level_off = np.zeros(len(sizes) + 1, dtype=np.int64)
-    np.cumsum(np.asarray(sizes, dtype=np.int64), out=level_off[1:])
+    np.cumsum(sizes, out=level_off[1:])
     return item_level_off, level_off, flat
 
 
