@@ -55,6 +55,25 @@ typedef struct nsm_pair {
     double score;
 } nsm_pair_t;
 
+/* out_mode: how kept pairs are written */
+#define NSM_OUT_PAIRS 0   /* out_pairs is nsm_pair_t[out_capacity]: 16 bytes per kept pair (default) */
+#define NSM_OUT_PACKETS 1 /* out_pairs is nsm_packet_t[out_capacity] (nsm_jaccard_allpairs only):
+                             ~10.4 bytes per kept pair for results that are bound by the
+                             device->host link.  The kept pairs of one packet lie in one
+                             512 x 128 block of the cross product. */
+#define NSM_PACKET_RECORDS 48
+
+/* Up to 48 kept pairs of the block (left0 .. left0+511) x (right0 .. right0+127):
+ * pair i (i < count) is (left0 + (local[i] >> 7), right0 + (local[i] & 127), score[i]). */
+typedef struct nsm_packet {
+    uint32_t left0;
+    uint32_t right0;
+    uint32_t count;
+    uint32_t reserved_;
+    double score[NSM_PACKET_RECORDS];
+    uint16_t local[NSM_PACKET_RECORDS];
+} nsm_packet_t; /* 496 bytes */
+
 /* One cohort side for intersection_vs_union: CSR items -> levels -> sorted unique token ids
  * (layout and meaning: napkon_string_matching/gpu/pack.py).  Levels are what
  * ComparableData.gen_comp_value returns per item (comparable_data.py:283-285). */
@@ -112,18 +131,22 @@ typedef struct nsm_job {
     double threshold;     /* keep score >= threshold (float64 compare, comparable_data.py:243) */
     const uint64_t *l_cat; /* [left.n_items] category bit masks */
     const uint64_t *r_cat; /* [right.n_items] */
-    nsm_pair_t *out_pairs; /* [out_capacity], filled densely in no particular order */
+    void *out_pairs;       /* nsm_pair_t[out_capacity] or nsm_packet_t[out_capacity] (out_mode),
+                              16-byte aligned, filled densely in no particular order */
     uint64_t out_capacity;
-    uint64_t *out_count; /* number of kept pairs, also beyond capacity */
+    uint64_t *out_count; /* number of kept pairs (NSM_OUT_PACKETS: of packets), also beyond capacity */
     uint32_t *out_flags; /* NSM_FLAG_* */
-    uint64_t *out_stats; /* optional [NSM_N_STATS] counters, may be NULL */
+    uint64_t *out_stats; /* [NSM_N_STATS] counters; may be NULL with NSM_OUT_PAIRS */
+    uint32_t out_mode;   /* NSM_OUT_* */
+    uint32_t reserved_;
 } nsm_job_t;
 
 #define NSM_STAT_CANDIDATES 0   /* item pairs that reached exact float64 scoring */
 #define NSM_STAT_LEVEL_EVALS 1  /* score_func evaluations done exactly (popcount / merge / LCS) */
 #define NSM_STAT_LEVEL_MERGES 2 /* of those, ones that needed a token merge */
 #define NSM_STAT_BOUND_PAIRS 3  /* item pairs that reached the per-level bound (shared a signature bit) */
-#define NSM_N_STATS 4
+#define NSM_STAT_KEPT 4         /* kept pairs (== *out_count with NSM_OUT_PAIRS) */
+#define NSM_N_STATS 5
 
 int nsm_version(void);
 const char *nsm_last_error(void);

@@ -59,6 +59,10 @@ int prepare_job(const nsm_job_t *job, uint32_t n_left, cudaStream_t stream) {
         set_error("bad category mode or missing category masks");
         return NSM_ERR_BAD_ARG;
     }
+    if (job->out_mode > NSM_OUT_PACKETS) {
+        set_error("unknown out_mode %u", job->out_mode);
+        return NSM_ERR_BAD_ARG;
+    }
     if (reinterpret_cast<uintptr_t>(job->out_pairs) & 15u) {
         set_error("out_pairs must be 16-byte aligned");
         return NSM_ERR_BAD_ARG;

@@ -60,7 +60,10 @@ struct JaccardParams {
 struct __align__(16) JaccardSmem {
     ulonglong2 r_ht[J_SLOTS][JT_THREADS];  // (head, tail) per step of my right block
     ulonglong2 l_any[J_UNIT_LEFT];         // stage A word of every left item of the unit
-    nsm_pair_t out[J_WARPS][J_OUT];
+    union {
+        nsm_pair_t pairs[J_OUT];  // NSM_OUT_PAIRS: staged records of the warp
+        nsm_packet_t packet;      // NSM_OUT_PACKETS: the packet the warp is filling
+    } out[J_WARPS];
     uint32_t r_info[J_SLOTS][JT_THREADS];  // size | fold count << 16
     uint32_t r_k[JT_THREADS];
     float rcp_up[J_RCP];
@@ -240,15 +243,16 @@ jaccard_allpairs_kernel(const JaccardParams p) {
     if (tid < NSM_N_STATS) s.stats[tid] = 0;
     if (tid == 0) mbar_init(&s.bar, 1);
     uint32_t bar_parity = 0;
-    unsigned long long st_cand = 0, st_evals = 0, st_merges = 0, st_bound = 0;
+    unsigned long long st_cand = 0, st_evals = 0, st_merges = 0, st_bound = 0, st_kept = 0;
     uint32_t out_n = 0;  // warp-uniform fill of s.out[warp]
+    const bool packets = p.job.out_mode == NSM_OUT_PACKETS;
 
     auto flush_out = [&]() {
         if (out_n == 0) return;
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(count, (unsigned long long)out_n);
         base = __shfl_sync(FULL_MASK, base, 0);
-        const double2 *src = reinterpret_cast<const double2 *>(&s.out[warp][0]);
+        const double2 *src = reinterpret_cast<const double2 *>(&s.out[warp].pairs[0]);
         for (uint32_t i = lane; i < out_n; i += 32) {
             const unsigned long long pos = base + i;
             if (pos < p.job.out_capacity)
@@ -258,6 +262,28 @@ jaccard_allpairs_kernel(const JaccardParams p) {
         }
         __syncwarp();
         out_n = 0;
+    };
+    // NSM_OUT_PACKETS: the warp's packet goes out as 31 16-byte stores, one atomic per packet.
+    // Packets are filled to the last slot; only the one a warp holds at the end of a unit is partial.
+    auto flush_packet = [&](uint32_t n_rec, uint32_t l0, uint32_t r0) {
+        nsm_packet_t &pk = s.out[warp].packet;
+        unsigned long long pos = 0;
+        if (lane == 0) {
+            pk.left0 = l0; pk.right0 = r0; pk.count = n_rec; pk.reserved_ = 0;
+            pos = atomicAdd(count, 1ull);
+        }
+        __syncwarp();  // the header (and the callers' record stores) before the vector reads below
+        pos = __shfl_sync(FULL_MASK, pos, 0);
+        if (pos < p.job.out_capacity) {
+            constexpr uint32_t VECS = sizeof(nsm_packet_t) / 16;
+            static_assert(sizeof(nsm_packet_t) == 496 && VECS <= 32, "one 16-byte vector per lane");
+            if (lane < VECS)
+                reinterpret_cast<uint4 *>(reinterpret_cast<nsm_packet_t *>(p.job.out_pairs) + pos)[lane] =
+                    reinterpret_cast<const uint4 *>(&pk)[lane];
+        } else if (lane == 0) {
+            atomicOr(p.job.out_flags, NSM_FLAG_OVERFLOW);
+        }
+        __syncwarp();
     };
 
     // summary of one item at step t >= 1: from the slot arrays, or from the CSR arrays when the
@@ -658,27 +684,52 @@ jaccard_allpairs_kernel(const JaccardParams p) {
                 const bool keep = ok && score >= thr;
                 const unsigned m = __ballot_sync(FULL_MASK, keep);
                 if (m) {
-                    const uint32_t n = __popc(m);
-                    if (out_n + n > J_OUT) flush_out();
-                    if (keep) {
-                        double2 rec;
-                        rec.x = __longlong_as_double((long long)(((unsigned long long)c_r << 32) | c_l));
-                        rec.y = score;
-                        reinterpret_cast<double2 *>(&s.out[warp][0])[out_n + __popc(m & lanemask_lt())] = rec;
+                    const uint32_t n = __popc(m), slot = out_n + __popc(m & lanemask_lt());
+                    st_kept += keep ? 1u : 0u;
+                    if (packets) {
+                        // unit-local 16-bit position + score; the packet is filled to its last slot
+                        nsm_packet_t &pk = s.out[warp].packet;
+                        const uint16_t loc = (uint16_t)((li << 7) | rc);
+                        if (keep && slot < (uint32_t)NSM_PACKET_RECORDS) { pk.score[slot] = score; pk.local[slot] = loc; }
+                        if (out_n + n >= (uint32_t)NSM_PACKET_RECORDS) {
+                            __syncwarp();
+                            flush_packet(NSM_PACKET_RECORDS, l0, r0);
+                            if (keep && slot >= (uint32_t)NSM_PACKET_RECORDS) {
+                                pk.score[slot - NSM_PACKET_RECORDS] = score;
+                                pk.local[slot - NSM_PACKET_RECORDS] = loc;
+                            }
+                            out_n = out_n + n - NSM_PACKET_RECORDS;
+                        } else {
+                            out_n += n;
+                        }
+                    } else {
+                        if (out_n + n > J_OUT) flush_out();
+                        if (keep) {
+                            double2 rec;
+                            rec.x = __longlong_as_double((long long)(((unsigned long long)c_r << 32) | c_l));
+                            rec.y = score;
+                            reinterpret_cast<double2 *>(&s.out[warp].pairs[0])[out_n + __popc(m & lanemask_lt())] = rec;
+                        }
+                        out_n += n;
                     }
-                    out_n += n;
                 }
                 __syncwarp();
             }
         }
+        if (packets && out_n) {  // positions are unit-local: the warp's partial packet ends here
+            __syncwarp();
+            flush_packet(out_n, l0, r0);
+            out_n = 0;
+        }
     }
-    flush_out();
+    if (!packets) flush_out();
 
     if (p.job.out_stats) {
         atomicAdd(&s.stats[NSM_STAT_CANDIDATES], st_cand);
         atomicAdd(&s.stats[NSM_STAT_LEVEL_EVALS], st_evals);
         atomicAdd(&s.stats[NSM_STAT_LEVEL_MERGES], st_merges);
         atomicAdd(&s.stats[NSM_STAT_BOUND_PAIRS], st_bound);
+        atomicAdd(&s.stats[NSM_STAT_KEPT], st_kept);
         __syncthreads();
         if (tid < NSM_N_STATS && s.stats[tid])
             atomicAdd(reinterpret_cast<unsigned long long *>(p.job.out_stats) + tid, s.stats[tid]);
@@ -716,6 +767,10 @@ extern "C" int nsm_jaccard_allpairs(const nsm_sets_t *left, const nsm_sets_t *ri
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (!left || !right || !job) { set_error("null argument"); return NSM_ERR_BAD_ARG; }
     if (int rc = prepare_job(job, left->n_items, stream)) return rc;
+    if (job->out_mode == NSM_OUT_PACKETS && !job->out_stats) {
+        set_error("NSM_OUT_PACKETS needs out_stats (the kept-pair count is NSM_STAT_KEPT)");
+        return NSM_ERR_BAD_ARG;
+    }
     if (job->l_row_begin == job->l_row_end || right->n_items == 0) return NSM_OK;
     if (job->flat && (left->max_levels > 1 || right->max_levels > 1)) {
         set_error("flat scoring needs items with exactly one level");

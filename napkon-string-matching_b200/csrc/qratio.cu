@@ -365,8 +365,9 @@ qratio_allpairs_kernel(const QratioParams p) {
                 s_lev_off[g] = __ldg(p.L.level_chr_off + G0 + g) - C0;
                 s_lev_len[g] = __ldg(p.L.level_len + G0 + g);
             }
-            if (tid <= nl) s_item_g0[tid] = __ldg(p.L.item_level_off + l0 + tid) - G0;
-            if (tid < nl) s_cat[tid] = p.job.cat_mode ? __ldg(p.job.l_cat + l0 + tid) : 0;
+            // strided: a launch may run fewer threads than the tile has items (small right sides)
+            for (uint32_t i = tid; i <= nl; i += nthr) s_item_g0[i] = __ldg(p.L.item_level_off + l0 + i) - G0;
+            for (uint32_t i = tid; i < nl; i += nthr) s_cat[i] = p.job.cat_mode ? __ldg(p.job.l_cat + l0 + i) : 0;
             __syncthreads();
 
             if (!LEVELS) {
@@ -384,7 +385,7 @@ qratio_allpairs_kernel(const QratioParams p) {
                         atomicOr(p.job.out_flags, NSM_FLAG_EMPTY_ITEM);
                         ok = false;
                     }
-                    emit_pairs(ok && score >= thr, l0 + li, r, score, p.job.out_pairs,
+                    emit_pairs(ok && score >= thr, l0 + li, r, score, static_cast<nsm_pair_t *>(p.job.out_pairs),
                                p.job.out_capacity, count, p.job.out_flags);
                 };
                 // (uniform control flow; threads without a right level compute on stale masks, unused)
@@ -475,7 +476,7 @@ qratio_allpairs_kernel(const QratioParams p) {
                         ok = false;
                     }
                     const double score = s_acc[(size_t)li * nthr + tid];
-                    emit_pairs(ok && score >= thr, l0 + li, r, score, p.job.out_pairs,
+                    emit_pairs(ok && score >= thr, l0 + li, r, score, static_cast<nsm_pair_t *>(p.job.out_pairs),
                                p.job.out_capacity, count, p.job.out_flags);
                 }
             }
@@ -520,6 +521,10 @@ extern "C" int nsm_qratio_allpairs(const nsm_strings_t *left, const nsm_strings_
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (!left || !right || !job) { set_error("null argument"); return NSM_ERR_BAD_ARG; }
     if (int rc = prepare_job(job, left->n_items, stream)) return rc;
+    if (job->out_mode != NSM_OUT_PAIRS) {
+        set_error("nsm_qratio_allpairs writes nsm_pair_t records only (out_mode NSM_OUT_PAIRS)");
+        return NSM_ERR_UNSUPPORTED;
+    }
     if (job->l_row_begin == job->l_row_end || right->n_items == 0) return NSM_OK;
     if (job->flat && (left->max_levels > 1 || right->max_levels > 1)) {
         set_error("flat scoring needs items with exactly one level");

@@ -8,8 +8,9 @@ records themselves are concatenated on the host through a gloo group.
 from __future__ import annotations
 
 import contextlib
+import os
 import threading
-from typing import Callable, List, Tuple
+from typing import Callable, List, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -84,10 +85,62 @@ def allgather_counts(count: int) -> List[int]:
     return [int(t.item()) for t in everyone]
 
 
+def allgather_count_vectors(counts: Sequence[int]) -> List[List[int]]:
+    """:func:`allgather_counts` for several counters at once: ``result[rank][k]``."""
+    rank, world = _world()
+    if world == 1:
+        return [[int(c) for c in counts]]
+    device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" \
+        else torch.device("cpu")
+    mine = torch.tensor([int(c) for c in counts], dtype=torch.int64, device=device)
+    everyone = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(everyone, mine)
+    return [[int(v) for v in t.tolist()] for t in everyone]
+
+
+def sharded_run_jobs(engine, jobs, *, to_host: bool = True, decode: bool = True, copy: bool = True):
+    """Several comparisons, each split over the ranks by left row blocks, through ONE
+    ``engine.run_jobs`` call per rank (so the copy-out of one comparison runs beside the kernel of
+    the next), followed by the path's one collective: the all-gather of the kept-pair counts.
+
+    ``jobs`` are ``engine.Job``s over whole cohorts (or a ``rows`` range); every rank must pass the
+    same list.  Returns ``(outs, counts)``: this rank's records per job (they stay sharded — each
+    rank holds the pairs of its own rows) and ``counts[rank][job]``."""
+    import dataclasses
+
+    rank, world = _world()
+    mine = []
+    for job in jobs:
+        begin, end = job.rows if job.rows is not None else (0, job.left.n_items)
+        b, e = partition_rows(job.left.weights[begin:end], world)[rank]
+        mine.append(dataclasses.replace(job, rows=(begin + b, begin + e)))
+    failure = None
+    try:
+        outs = engine.run_jobs(mine, to_host=to_host, decode=decode, copy=copy)
+        kept = [info["count"] for info in engine.last_infos]
+    except Exception as exc:  # noqa: BLE001 - the other ranks wait in the collective below
+        failure, outs, kept = exc, [], [-1] * len(jobs)
+    counts = allgather_count_vectors(kept)
+    if failure is not None:
+        raise failure
+    for r, row in enumerate(counts):
+        if min(row, default=0) < 0:
+            raise RuntimeError(f"scoring the row blocks of rank {r} failed")
+    return outs, counts
+
+
+def default_gather() -> str:
+    """Where the records of a row-sharded comparison end up: "rank0" (rank 0 holds the complete
+    result, every other rank the pairs of its own rows; exact-size point-to-point transfers, no
+    redundant traffic), "all" (identical on every rank) or "none".  ``NSM_GATHER`` overrides."""
+    return os.environ.get("NSM_GATHER", "rank0")
+
+
 def sharded_all_pairs(score_block: Callable[[int, int], np.ndarray], weights: np.ndarray,
-                      gather: bool = True) -> np.ndarray:
-    """Runs ``score_block(begin, end)`` on this rank's row block and returns the records of all
-    ranks (``gather=True``, identical on every rank) or only this rank's."""
+                      gather=None) -> np.ndarray:
+    """Runs ``score_block(begin, end)`` on this rank's row block, all-gathers the kept-pair counts
+    and returns records according to ``gather`` (see :func:`default_gather`; True means "all",
+    False "none")."""
     global last_counts
     rank, world = _world()
     n = len(weights)
@@ -95,6 +148,11 @@ def sharded_all_pairs(score_block: Callable[[int, int], np.ndarray], weights: np
         out = score_block(0, n)
         last_counts = [len(out)]
         return out
+    if gather is None:
+        gather = default_gather()
+    gather = {True: "all", False: "none"}.get(gather, gather)
+    if gather not in ("all", "rank0", "none"):
+        raise ValueError(f"gather={gather!r}")
     begin, end = partition_rows(weights, world)[rank]
     failure = None
     try:
@@ -108,12 +166,25 @@ def sharded_all_pairs(score_block: Callable[[int, int], np.ndarray], weights: np
     if min(counts) < 0:
         raise RuntimeError(f"scoring the row block of rank {counts.index(-1)} failed")
     last_counts = counts
-    if not gather:
+    if gather == "none" or max(counts) == 0:
         return mine
     group = _get_host_group()
+    mine = np.ascontiguousarray(mine)
+    if gather == "rank0":
+        # exact-size transfers to rank 0 only: every record crosses the host once
+        if rank != 0:
+            if len(mine):
+                dist.send(torch.from_numpy(mine.view(np.uint8)), dst=0, group=group)
+            return mine
+        out = np.empty(sum(counts), dtype=PAIR_DTYPE)
+        out[: counts[0]] = mine
+        pos = counts[0]
+        for src in range(1, world):
+            if counts[src]:
+                dist.recv(torch.from_numpy(out[pos: pos + counts[src]].view(np.uint8)), src=src, group=group)
+                pos += counts[src]
+        return out
     cap = max(counts)
-    if cap == 0:
-        return np.zeros(0, dtype=PAIR_DTYPE)
     buf = np.zeros(cap, dtype=PAIR_DTYPE)
     buf[: len(mine)] = mine
     send = torch.from_numpy(buf.view(np.uint8))

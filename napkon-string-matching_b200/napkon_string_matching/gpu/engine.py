@@ -54,9 +54,42 @@ class Job:
     cat_mode: int = nsmlib.CAT_OFF
 
 
+class Records:
+    """Kept pairs of one job as they arrived from the device: views of the engine's pinned arena
+    (valid until its next call), part by part in the wire format of the part — ``PAIR_DTYPE``
+    records or ``nsm_packet_t`` packets (include/nsm.h)."""
+
+    def __init__(self, parts, count: int, left_perm=None, right_perm=None):
+        self.parts, self.count = parts, int(count)
+        self.left_perm, self.right_perm = left_perm, right_perm
+
+    def __len__(self) -> int:
+        return self.count
+
+    @property
+    def nbytes(self) -> int:
+        return sum(a.nbytes for _, a in self.parts)
+
+    def decode(self, copy: bool = True) -> np.ndarray:
+        """All parts as one ``PAIR_DTYPE`` array with the callers' item indices."""
+        if not self.parts:
+            return np.zeros(0, dtype=PAIR_DTYPE)
+        arrays = [nsmlib.decode_packets(a) if mode == nsmlib.OUT_PACKETS else a for mode, a in self.parts]
+        if len(arrays) == 1:
+            plain = self.parts[0][0] == nsmlib.OUT_PAIRS
+            out = arrays[0].copy() if (plain and (copy or self.left_perm is not None)) else arrays[0]
+        else:
+            out = np.concatenate(arrays)
+        if self.left_perm is not None:   # stored positions -> the caller's item indices
+            out["left"] = self.left_perm[out["left"]]
+        if self.right_perm is not None:
+            out["right"] = self.right_perm[out["right"]]
+        return out
+
+
 class Engine:
     PIPELINE_BLOCK_BYTES = 512 << 20
-    PIPELINE_MIN_PAIRS = 1 << 30   # smaller jobs are one launch: splitting them costs more than it hides
+    PIPELINE_MIN_PAIRS = 1 << 26   # smaller jobs are one launch: a probe costs more than it saves
 
     def __init__(self, device: Optional[int] = None, max_pairs_per_block: int = 1 << 30):
         _require_cuda()
@@ -64,6 +97,9 @@ class Engine:
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         self.max_pairs_per_block = int(max_pairs_per_block)
         self.pipeline_d2h = True    # probe + row blocks for results that go to the host
+        # record format of dense results that go to the host: "auto" (packets when the probe block
+        # finds >= 2 packets per warp and unit), True (packets for every token-set job), False
+        self.compact = "auto"
         self._buffers: Dict[str, torch.Tensor] = {}
         self.launches = 0           # kernels of ours launched so far
         self.time_kernels = False   # bracket every comparison kernel with CUDA events
@@ -169,7 +205,7 @@ class Engine:
         return out
 
     def run_jobs(self, jobs: List["Job"], *, capacity: Optional[int] = None, to_host: bool = True,
-                 copy: bool = True) -> List[np.ndarray]:
+                 copy: bool = True, decode: bool = True):
         """Runs several all-pairs jobs back to back.
 
         One kernel launch covers a whole job; kept records are compacted into one of two device
@@ -178,13 +214,15 @@ class Engine:
         exactly: the arena is grown to the exact need and the launch repeated once.  A job that
         keeps more than ``max_pairs_per_block`` records is split into left row blocks.
         ``to_host=False`` leaves the records on the device (kernel-only timing) and returns empty
-        arrays; ``copy=False`` returns views of the pinned arena (valid until the next call)."""
+        arrays; ``copy=False`` returns views of the pinned arena (valid until the next call);
+        ``decode=False`` returns :class:`Records` (the parts in their wire format) instead of
+        ``PAIR_DTYPE`` arrays."""
         # the C ABI launches on the calling thread's current device: make it this engine's
         with torch.cuda.device(self.device):
-            return self._run_jobs(jobs, capacity, to_host, copy)
+            return self._run_jobs(jobs, capacity, to_host, copy, decode)
 
-    def _run_jobs(self, jobs: List["Job"], capacity: Optional[int], to_host: bool, copy: bool
-                  ) -> List[np.ndarray]:
+    def _run_jobs(self, jobs: List["Job"], capacity: Optional[int], to_host: bool, copy: bool,
+                  decode: bool = True):
         stream = torch.cuda.current_stream(self.device)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
@@ -192,45 +230,59 @@ class Engine:
         ctl = [self._arena(f"ctl{i}", 64, pinned=False) for i in range(2)]
         ctl_pin = [self._arena(f"ctl_pin{i}", 64, pinned=True) for i in range(2)]
         slot_free: List[Optional[torch.cuda.Event]] = [None, None]   # D2H out of the arena done
+        rec_bytes = (16, nsmlib.PACKET_DTYPE.itemsize)
 
-        # expand jobs into row-block work items: (job index, begin, end).  A job whose records go
-        # to the host starts with a PROBE block (1/8 of its rows): its kept-pair density decides
-        # into how many blocks the rest is cut, so that the device->host copy of a large result
-        # starts early and runs beside the remaining kernels instead of after one long launch.
-        probes = set()
-        work: List[Tuple[int, int, int]] = []
+        def n_units(rows: int, n_right: int) -> int:
+            return -(-rows // nsmlib.UNIT_LEFT) * -(-n_right // nsmlib.UNIT_RIGHT)
+
+        def capacity_for(mode: int, records: float, rows: int, n_right: int) -> int:
+            """Arena entries (pairs or packets) that hold `records` kept pairs of a row block."""
+            records = min(float(self.max_pairs_per_block), records)
+            if mode == nsmlib.OUT_PACKETS:   # full packets + at most one partial per warp and unit
+                return int(records / nsmlib.PACKET_RECORDS) + 4 * n_units(rows, n_right) + 64
+            return max(int(records) + 4096, 1 << 18)
+
+        # Work items: row blocks of the jobs.  A job whose records go to the host starts with a
+        # small PROBE block: its kept-pair density sizes the arenas of the rest exactly (no
+        # overflow re-run), picks the record format (16-byte pairs, or packets when the result is
+        # dense enough to be bound by the device->host link) and cuts the rest into blocks so that
+        # the copy-out of one block runs beside the kernel of the next.
+        work: List[dict] = []
         infos = []
         for j, job in enumerate(jobs):
             if job.left.kind != job.right.kind:
                 raise TypeError("left and right must be packed for the same score function")
             begin, end = job.rows if job.rows is not None else (0, job.left.n_items)
             infos.append({"count": 0, "flags": 0, "reruns": 0, "blocks": 0, "d2h_bytes": 0,
-                          "stats": dict.fromkeys(nsmlib.STAT_NAMES, 0),
+                          "packets": 0, "stats": dict.fromkeys(nsmlib.STAT_NAMES, 0),
                           "item_pairs": max(0, end - begin) * job.right.n_items, "parts": []})
-            if end > begin and job.right.n_items:
-                rows = end - begin
-                if (to_host and self.pipeline_d2h and capacity is None and rows >= 8 * 1024
-                        and rows * job.right.n_items >= self.PIPELINE_MIN_PAIRS):
-                    cut = begin + rows // 8
-                    probes.add((j, begin, cut))
-                    work += [(j, begin, cut), (j, cut, end)]
-                else:
-                    work.append((j, begin, end))
+            if end <= begin or not job.right.n_items:
+                continue
+            rows = end - begin
+            forced = nsmlib.OUT_PACKETS if (self.compact is True and job.left.kind == "sets") else nsmlib.OUT_PAIRS
+            if (to_host and self.pipeline_d2h and capacity is None and rows >= 4 * nsmlib.UNIT_LEFT
+                    and rows * job.right.n_items >= self.PIPELINE_MIN_PAIRS):
+                cut = begin + max(nsmlib.UNIT_LEFT, rows // 16 // nsmlib.UNIT_LEFT * nsmlib.UNIT_LEFT)
+                work.append({"j": j, "rb": begin, "re": cut, "mode": nsmlib.OUT_PAIRS, "probe": True})
+                work.append({"j": j, "rb": cut, "re": end, "mode": forced, "rest": True})
+            else:
+                work.append({"j": j, "rb": begin, "re": end, "mode": forced})
         self.last_infos = infos
 
-        def launch(slot: int, item: Tuple[int, int, int], cap: int):
-            j, rb, re_ = item
-            job = jobs[j]
+        def launch(slot: int, item: dict):
+            job = jobs[item["j"]]
+            mode = item["mode"]
             fn = self.lib.nsm_jaccard_allpairs if job.left.kind == "sets" else self.lib.nsm_qratio_allpairs
             if slot_free[slot] is not None:
                 stream.wait_event(slot_free[slot])
-            dev = self._arena(f"out{slot}", cap * 16, pinned=False)
-            cap = dev.numel() // 16
+            dev = self._arena(f"out{slot}", item["cap"] * rec_bytes[mode], pinned=False)
+            cap = dev.numel() // rec_bytes[mode]
             c = ctl[slot]
-            cjob = nsmlib.NsmJob(rb, re_, int(job.flat), int(job.cat_mode), float(job.threshold),
+            cjob = nsmlib.NsmJob(item["rb"], item["re"], int(job.flat), int(job.cat_mode), float(job.threshold),
                                  job.l_cat.data_ptr() if job.l_cat is not None else None,
                                  job.r_cat.data_ptr() if job.r_cat is not None else None,
-                                 dev.data_ptr(), cap, c.data_ptr(), c.data_ptr() + 8, c.data_ptr() + 16)
+                                 dev.data_ptr(), cap, c.data_ptr(), c.data_ptr() + 8, c.data_ptr() + 16,
+                                 mode, 0)
             if self.time_kernels:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream)
@@ -245,78 +297,100 @@ class Engine:
             done.record(stream)
             return done
 
-        def default_capacity(item) -> int:
-            j, rb, re_ = item
-            have = max((self._buffers[k].numel() // 16 for k in ("out0", "out1") if k in self._buffers),
-                       default=0)
-            want = min(self.max_pairs_per_block, 1 << 24, max(1 << 16, (re_ - rb) * jobs[j].right.n_items // 8))
+        def default_capacity(item: dict) -> int:
+            job = jobs[item["j"]]
+            rows, n_right = item["re"] - item["rb"], job.right.n_items
+            if capacity is not None:
+                return capacity
+            have = max((self._buffers[k].numel() for k in ("out0", "out1") if k in self._buffers),
+                       default=0) // rec_bytes[item["mode"]]
+            want = capacity_for(item["mode"], min(1 << 24, max(1 << 16, rows * n_right // 8)), rows, n_right)
             return max(have, want)
 
+        def reserve_host(n_bytes: int, fill: int):
+            """The pinned arena holds `fill` bytes already and gets room for n_bytes more."""
+            pin = self._buffers.get("pin")
+            if pin is None or pin.numel() < fill + n_bytes:
+                copy_stream.synchronize()
+                grown = torch.empty(max(fill + n_bytes, (pin.numel() * 3 // 2) if pin is not None else 0),
+                                    dtype=torch.uint8).pin_memory()
+                if fill:
+                    grown[:fill].copy_(pin[:fill])
+                self._buffers["pin"] = pin = grown
+            return pin
+
         host_fill = 0
-        pending = None      # (slot, item, event, capacity)
+        pending = None      # (slot, item, event)
         queue = list(work)
         slot = 0
-        cap_hint = capacity
         while queue or pending:
             nxt = None
-            if pending is None and queue:
+            if pending is None:
                 item = queue.pop(0)
-                cap = cap_hint if cap_hint is not None else default_capacity(item)
-                pending = (slot, item, launch(slot, item, cap), cap)
+                item.setdefault("cap", default_capacity(item))
+                pending = (slot, item, launch(slot, item))
                 slot ^= 1
-            p_slot, p_item, p_done, p_cap = pending
+            p_slot, p_item, p_done = pending
             p_done.synchronize()
             words = ctl_pin[p_slot].numpy().view(np.uint64)
             count, flags = int(words[0]), int(words[1]) & 0xffffffff
             stats = [int(x) for x in words[2:2 + nsmlib.N_STATS]]
-            j, rb, re_ = p_item
-            info = infos[j]
+            j, rb, re_, mode = p_item["j"], p_item["rb"], p_item["re"], p_item["mode"]
+            job, info = jobs[j], infos[j]
+            kept = stats[nsmlib.STAT_NAMES.index("kept")] if mode == nsmlib.OUT_PACKETS else count
             if flags & nsmlib.FLAG_OVERFLOW:
+                # `count` is exact (pairs or packets): repeat with that size, or split the block
                 info["reruns"] += 1
-                if count > self.max_pairs_per_block and re_ - rb > 1:
-                    # split by the observed density so that every part should fit
-                    n_parts = min(re_ - rb, -(-count // max(1, self.max_pairs_per_block // 2)))
+                limit = self.max_pairs_per_block if mode == nsmlib.OUT_PAIRS else \
+                    max(1, self.max_pairs_per_block * 16 // rec_bytes[mode])
+                if count > limit and re_ - rb > 1:
+                    n_parts = min(re_ - rb, -(-count // max(1, limit // 2)))
                     cuts = np.linspace(rb, re_, n_parts + 1).astype(np.int64)
-                    queue[:0] = [(j, int(a), int(b)) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
-                    cap_hint = self.max_pairs_per_block
+                    queue[:0] = [{"j": j, "rb": int(a), "re": int(b), "mode": mode, "cap": limit}
+                                 for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
                 else:
-                    queue.insert(0, p_item)
-                    cap_hint = int(count * 1.02) + 1024
+                    queue.insert(0, {**p_item, "cap": int(count * 1.02) + 1024})
                 pending = None
                 slot = p_slot
                 continue
-            if p_item in probes and queue and queue[0][0] == j:
-                # cut the rest of the job into blocks of about PIPELINE_BLOCK_BYTES of records
-                _, rest_b, rest_e = queue.pop(0)
-                density = count / max(1, re_ - rb)
-                expect = density * (rest_e - rest_b) * 16
-                n_parts = int(min(16, max(1, -(-expect // self.PIPELINE_BLOCK_BYTES))))
-                cuts = np.linspace(rest_b, rest_e, n_parts + 1).astype(np.int64)
-                queue[:0] = [(j, int(a), int(b)) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
-                if n_parts > 1 or cap_hint is None:
-                    need = int(density * (int(cuts[1]) - int(cuts[0])) * 1.1) + 4096
-                    cap_hint = max(cap_hint or 0, min(self.max_pairs_per_block, need))
-            # launch the next job before copying this one out, so that the two overlap
+            if p_item.get("probe") and queue and queue[0].get("rest") and queue[0]["j"] == j:
+                rest = queue.pop(0)
+                rest_rows = rest["re"] - rest["rb"]
+                density = kept / max(1, (re_ - rb) * job.right.n_items)
+                expect = density * rest_rows * job.right.n_items        # kept pairs still to come
+                r_mode = rest["mode"]
+                if (self.compact == "auto" and job.left.kind == "sets" and
+                        density * nsmlib.UNIT_LEFT * 32 >= 2 * nsmlib.PACKET_RECORDS):
+                    r_mode = nsmlib.OUT_PACKETS   # >= two packets per warp and unit: < 14 B per pair
+                per_rec = 16 if r_mode == nsmlib.OUT_PAIRS else rec_bytes[1] / nsmlib.PACKET_RECORDS
+                n_parts = int(min(16, max(1, -(-(expect * per_rec) // self.PIPELINE_BLOCK_BYTES))))
+                step = -(-rest_rows // n_parts)
+                step = -(-step // nsmlib.UNIT_LEFT) * nsmlib.UNIT_LEFT   # whole 512-row chunks
+                cuts = list(range(rest["rb"], rest["re"], step)) + [rest["re"]]
+                margin = 1.15 if expect > 1e6 else 2.0
+                queue[:0] = [{"j": j, "rb": a, "re": b, "mode": r_mode,
+                              "cap": capacity_for(r_mode, density * (b - a) * job.right.n_items * margin + 4096,
+                                                  b - a, job.right.n_items)}
+                             for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+                if to_host:   # one allocation of page-locked memory for everything still to come
+                    ahead = sum(q["cap"] * rec_bytes[q["mode"]] for q in queue if q["j"] == j and "cap" in q)
+                    reserve_host(count * 16 + ahead, host_fill)
+            # launch the next block before copying this one out, so that the two overlap
             if queue:
                 item = queue.pop(0)
-                cap = cap_hint if cap_hint is not None else default_capacity(item)
-                nxt = (slot, item, launch(slot, item, cap), cap)
+                item.setdefault("cap", default_capacity(item))
+                nxt = (slot, item, launch(slot, item))
                 slot ^= 1
-            info["count"] += count
+            info["count"] += kept
             info["flags"] |= flags
             info["blocks"] += 1
             for name, v in zip(nsmlib.STAT_NAMES, stats):
                 info["stats"][name] += v
+            if mode == nsmlib.OUT_PACKETS:
+                info["packets"] += count
             if to_host and count:
-                n_bytes = count * 16
-                pin = self._buffers.get("pin")
-                if pin is None or pin.numel() < host_fill + n_bytes:
-                    copy_stream.synchronize()
-                    grown = torch.empty(max(host_fill + n_bytes, 2 * (pin.numel() if pin is not None else 0)),
-                                        dtype=torch.uint8).pin_memory()
-                    if host_fill:
-                        grown[:host_fill].copy_(pin[:host_fill])
-                    self._buffers["pin"] = pin = grown
+                n_bytes = count * rec_bytes[mode]
+                pin = reserve_host(n_bytes, host_fill)
                 copy_stream.wait_event(p_done)
                 with torch.cuda.stream(copy_stream):
                     pin[host_fill:host_fill + n_bytes].copy_(self._buffers[f"out{p_slot}"][:n_bytes],
@@ -324,7 +398,7 @@ class Engine:
                     freed = torch.cuda.Event()
                     freed.record(copy_stream)
                 slot_free[p_slot] = freed
-                info["parts"].append((host_fill, n_bytes))
+                info["parts"].append((host_fill, n_bytes, mode))
                 info["d2h_bytes"] += n_bytes
                 host_fill += n_bytes
             pending = nxt
@@ -339,22 +413,14 @@ class Engine:
             self._timed.clear()
 
         outs = []
-        for info in infos:
+        for job, info in zip(jobs, infos):
             parts = info.pop("parts")
-            if not to_host or not parts:
-                outs.append(np.zeros(0, dtype=PAIR_DTYPE))
-                continue
-            pin = self._buffers["pin"]
-            # the parts of one job are adjacent in the pinned arena
-            lo, hi = parts[0][0], parts[-1][0] + parts[-1][1]
-            view = pin[lo:hi].numpy().view(PAIR_DTYPE)
-            out = view.copy() if copy else view
-            job = jobs[len(outs)]
-            if job.left.perm is not None:   # stored positions -> the caller's item indices
-                out["left"] = job.left.perm[out["left"]]
-            if job.right.perm is not None:
-                out["right"] = job.right.perm[out["right"]]
-            outs.append(out)
+            pin = self._buffers.get("pin")
+            views = [(mode, pin[lo:lo + n].numpy().view(PAIR_DTYPE if mode == nsmlib.OUT_PAIRS
+                                                        else nsmlib.PACKET_DTYPE))
+                     for lo, n, mode in parts] if to_host else []
+            rec = Records(views, info["count"] if to_host else 0, job.left.perm, job.right.perm)
+            outs.append(rec.decode(copy=copy) if decode else rec)
         return outs
 
     # ------------------------------------------------------------------ roofline denominators

@@ -15,11 +15,32 @@ LIB_PATH = pathlib.Path(os.environ.get("NSM_B200_LIB") or _HERE / "libnsm_b200.s
 NSM_OK = 0
 FLAG_OVERFLOW, FLAG_ZERO_UNION, FLAG_EMPTY_ITEM = 1, 2, 4
 CAT_OFF, CAT_LIST_LIST, CAT_MEMBER = 0, 1, 2
-N_STATS = 4
-STAT_NAMES = ("candidates", "level_evals", "level_merges", "bound_pairs")
+N_STATS = 5
+STAT_NAMES = ("candidates", "level_evals", "level_merges", "bound_pairs", "kept")
 
 PAIR_DTYPE = np.dtype([("left", np.uint32), ("right", np.uint32), ("score", np.float64)])
 assert PAIR_DTYPE.itemsize == 16
+
+# NSM_OUT_PACKETS (include/nsm.h:nsm_packet_t): up to 48 kept pairs of one 512 x 128 block
+OUT_PAIRS, OUT_PACKETS = 0, 1
+PACKET_RECORDS = 48
+PACKET_DTYPE = np.dtype([("left0", np.uint32), ("right0", np.uint32), ("count", np.uint32),
+                         ("reserved_", np.uint32), ("score", np.float64, (PACKET_RECORDS,)),
+                         ("local", np.uint16, (PACKET_RECORDS,))])
+assert PACKET_DTYPE.itemsize == 496
+UNIT_LEFT, UNIT_RIGHT = 512, 128   # the block of the cross product one packet lies in
+
+
+def decode_packets(packets: np.ndarray) -> np.ndarray:
+    """``nsm_packet_t`` records -> ``PAIR_DTYPE`` records (host side of NSM_OUT_PACKETS)."""
+    count = packets["count"].astype(np.int64)
+    used = np.arange(PACKET_RECORDS, dtype=np.int64)[None, :] < count[:, None]
+    out = np.empty(int(count.sum()), dtype=PAIR_DTYPE)
+    local = packets["local"][used].astype(np.uint32)
+    out["left"] = np.repeat(packets["left0"], count) + (local >> np.uint32(7))
+    out["right"] = np.repeat(packets["right0"], count) + (local & np.uint32(127))
+    out["score"] = packets["score"][used]
+    return out
 
 RAW_SUFFIX_PARTS, RAW_LEVELS = 0, 1
 PACK_MAX_ITEM_IDS = 1024
@@ -58,7 +79,8 @@ class NsmJob(C.Structure):
     _fields_ = [("l_row_begin", C.c_uint32), ("l_row_end", C.c_uint32), ("flat", C.c_uint32),
                 ("cat_mode", C.c_uint32), ("threshold", C.c_double), ("l_cat", C.c_void_p),
                 ("r_cat", C.c_void_p), ("out_pairs", C.c_void_p), ("out_capacity", C.c_uint64),
-                ("out_count", C.c_void_p), ("out_flags", C.c_void_p), ("out_stats", C.c_void_p)]
+                ("out_count", C.c_void_p), ("out_flags", C.c_void_p), ("out_stats", C.c_void_p),
+                ("out_mode", C.c_uint32), ("reserved_", C.c_uint32)]
 
 
 class NsmError(RuntimeError):

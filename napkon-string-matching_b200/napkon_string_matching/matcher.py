@@ -155,11 +155,25 @@ class Matcher:
             }
         return result
 
+    @staticmethod
+    def _reports() -> bool:
+        """Under torch.distributed only rank 0 reports: with row-sharded comparisons it is the
+        rank that holds the complete results (gpu/distributed.py:default_gather)."""
+        try:
+            import torch.distributed as dist
+        except ImportError:
+            return True
+        return not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0
+
     def print_analysis(self) -> None:
+        if not self._reports():
+            return
         for name, item in self._analyse().items():
             logger.info("%s\t%s", name, "\t".join(f"{k}: {v}" for k, v in item.items()))
 
     def write_results(self) -> None:
+        if not self._reports():
+            return
         matching = self.config[CONFIG_FIELD_MATCHING]
         output_file = RESULTS_FILE_PATTERN.format(
             **{**matching, "score_func": matching["score_func"].replace("_", "-")})

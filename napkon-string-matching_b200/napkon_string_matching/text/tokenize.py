@@ -13,6 +13,7 @@ the middle.  Tokenisation runs once per item on the host, never per pair.
 """
 from __future__ import annotations
 
+import logging
 import re
 from functools import lru_cache
 from typing import Iterable, List
@@ -131,7 +132,14 @@ def _treebank(sentence: str) -> List[str]:
     return text.split()
 
 
-_SIMPLE = re.compile(r"^[\w \t\n\r\-/+]*$")  # nothing any rule above would touch
+_SIMPLE = re.compile(r"^[\w \t\n\r\-/+]*$")  # nothing any rule above would touch ...
+# ... except the apostrophe-free contractions of _CONTRACT2, which the Treebank rules split in two
+_CONTRACTION_WORD = re.compile(r"(?i)\b(?:cannot|gimme|gonna|gotta|lemme|wanna)\b")
+
+
+def _is_simple(text: str) -> bool:
+    return (_SIMPLE.match(text) is not None and "--" not in text
+            and _CONTRACTION_WORD.search(text) is None)
 
 
 _nltk_word_tokenize = None   # nltk's tokeniser once resolved; False when nltk cannot be used
@@ -149,6 +157,11 @@ def _resolve_nltk():
             _nltk_word_tokenize = fn
         except Exception:  # noqa: BLE001 - not installed, or its data files are missing
             _nltk_word_tokenize = False
+            logging.getLogger(__name__).warning(
+                "nltk (with its punkt data) is not usable: tokenising with the built-in restatement "
+                "of the Treebank word tokeniser and a crude sentence splitter; token sets of texts "
+                "with abbreviations or unusual punctuation can differ from the reference's. "
+                "Install nltk~=3.7 and its 'punkt' + 'stopwords' data for exact reference behaviour.")
     return _nltk_word_tokenize
 
 
@@ -157,7 +170,7 @@ def word_tokenize(text: str) -> List[str]:
     fn = _resolve_nltk()
     if fn:
         return fn(text)
-    if _SIMPLE.match(text) and "--" not in text:
+    if _is_simple(text):
         return text.split()
     out: List[str] = []
     for sent in _split_sentences(text):
@@ -208,7 +221,7 @@ def _gen_comp_value_simple(items):
     levels = []
     for part in reversed(items):                       # the part that enters at the next level
         for text in (part if isinstance(part, list) else (part,)):
-            if not isinstance(text, str) or "--" in text or not _SIMPLE.match(text):
+            if not isinstance(text, str) or not _is_simple(text):
                 return None
             for w in text.split():
                 folded = w.casefold()

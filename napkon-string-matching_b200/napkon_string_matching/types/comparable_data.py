@@ -13,6 +13,7 @@ here the items are tokenised and packed on the host, every pair is scored on the
 from __future__ import annotations
 
 import logging
+import os
 from enum import Enum
 from pathlib import Path
 from typing import Dict, List, Tuple
@@ -32,6 +33,47 @@ COMP_COLUMN = "Compare"
 
 logger = logging.getLogger(__name__)
 flatten_list = _tok.flatten_list
+
+
+def _sharded_world():
+    """(rank, world) when the ranks of a torch.distributed job share ONE comparison by row
+    blocks (gpu/distributed.py); (0, 1) for a single process or when the scheduler has dealt out
+    whole comparisons."""
+    try:
+        from napkon_string_matching.gpu import distributed
+    except ImportError:  # torch missing: single process
+        return 0, 1
+    return distributed._world()
+
+
+def _cache_decision(local_hit: bool):
+    """``(use the cache, this process writes the cache file)``.  With row-sharded ranks every rank
+    runs ``compare``; they must take the same branch (the miss branch holds a collective), so
+    rank 0's view of the cache directory decides for all and rank 0 alone writes."""
+    rank, world = _sharded_world()
+    if world == 1:
+        return local_hit, True
+    import torch.distributed as dist
+
+    from napkon_string_matching.gpu import distributed
+
+    box = [bool(local_hit)]
+    dist.broadcast_object_list(box, src=0, group=distributed.host_group())
+    return bool(box[0]), rank == 0
+
+
+def _share_cached(result):
+    """Rank 0's cached result for every row-sharded rank (the others may not see the file)."""
+    rank, world = _sharded_world()
+    if world == 1:
+        return result
+    import torch.distributed as dist
+
+    from napkon_string_matching.gpu import distributed
+
+    box = [result if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=distributed.host_group())
+    return box[0]
 
 
 class ComparableColumns(Enum):
@@ -80,9 +122,13 @@ class ComparableData(Data):
             cache_threshold=cache_threshold,
         )
         cache_file = Path(cache_dir if cache_dir else "cache") / CACHE_FILE_PATTERN.format(df_hash)
-        if cached and cache_file.exists():
+        # row-sharded over torch.distributed ranks (gpu/distributed.py): every rank is in here, so
+        # rank 0 alone decides hit or miss (ranks may see different cache directories) and writes
+        use_cache, writer = _cache_decision(bool(cached) and cache_file.exists())
+        if use_cache:
             logger.info("using cached result")
-            result = Comparable.read_json(cache_file)
+            result = Comparable.read_json(cache_file) if cache_file.exists() else None
+            result = _share_cached(result)
         else:
             result = self.gen_comparable(
                 other,
@@ -95,9 +141,13 @@ class ComparableData(Data):
                 *args,
                 **kwargs,
             )
-            cache_file.parent.mkdir(parents=True, exist_ok=True)
-            logger.info("write cache to file")
-            result.write_json(cache_file)
+            if writer:
+                cache_file.parent.mkdir(parents=True, exist_ok=True)
+                logger.info("write cache to file")
+                # a reader never sees a half-written file: write aside, then rename
+                tmp = cache_file.with_name(f"{cache_file.name}.{os.getpid()}.tmp")
+                result.write_json(tmp)
+                os.replace(tmp, cache_file)
 
         # outside of the caching, so one cache serves several thresholds
         result = result[result.match_score >= score_threshold]

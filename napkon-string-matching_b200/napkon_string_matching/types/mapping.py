@@ -55,6 +55,13 @@ class Mapping:
     def __len__(self) -> int:
         return len(self._entries)
 
+    def __str__(self) -> str:
+        """Content-based and stable across processes.  ``ComparableData.compare`` hashes
+        ``str(mapping)`` into its cache key; the reference's Mapping has no ``__str__``, so its
+        key embeds ``object.__repr__`` — a memory address — and its compare cache can never hit in
+        another process.  Same content -> same key here."""
+        return "Mapping" + json.dumps(self.dict(), sort_keys=True, ensure_ascii=False)
+
     def __iter__(self) -> Iterator[Tuple[str, MappingEntry]]:
         return iter(self._entries.items())
 

@@ -171,3 +171,58 @@ void ora_score_pairs(int func, int flat, const ora_side_t *L, const ora_side_t *
     }
     if (flags_out) *flags_out = flags;
 }
+
+/* ---- CPU-baseline support only (oracle/shims/rapidfuzz, bench.py's reference arm) ------------
+ * rapidfuzz computes the Indel distance behind QRatio with a bit-parallel LCS in C++; a shim that
+ * ran the dynamic programme above would understate the reference's speed several times over.
+ * This is Hyyro's recurrence over 64-bit words on UTF-32 code points.  No parity check uses it
+ * (tests/test_oracle.py checks IT against the dynamic programme). */
+uint32_t ora_lcs_utf32(const uint32_t *a, uint32_t na, const uint32_t *b, uint32_t nb) {
+    enum { STACK_WORDS = 8, STACK_UNIQ = 128 };
+    uint32_t words, n_uniq = 0, i, w, lcs = 0;
+    uint64_t stack_masks[STACK_UNIQ * STACK_WORDS], stack_s[STACK_WORDS];
+    uint32_t stack_cp[STACK_UNIQ];
+    int16_t direct[256];
+    uint64_t *masks = stack_masks, *S = stack_s;
+    uint32_t *cps = stack_cp;
+    if (na == 0 || nb == 0) return 0;
+    if (na > nb) { const uint32_t *t = a; uint32_t tn = na; a = b; na = nb; b = t; nb = tn; }
+    words = (na + 63) / 64;
+    if (words > STACK_WORDS || na > STACK_UNIQ) {
+        masks = (uint64_t *)calloc((size_t)na * words + words, sizeof(uint64_t));
+        cps = (uint32_t *)malloc((size_t)na * sizeof(uint32_t));
+        S = masks + (size_t)na * words;
+    }
+    memset(direct, 0xff, sizeof(direct));
+    for (i = 0; i < na; i++) {
+        uint32_t c = a[i], k;
+        if (c < 256 && direct[c] >= 0) k = (uint32_t)direct[c];
+        else {
+            for (k = 0; k < n_uniq && cps[k] != c; k++) {}
+            if (k == n_uniq) {
+                cps[n_uniq++] = c;
+                for (w = 0; w < words; w++) masks[(size_t)k * words + w] = 0;
+                if (c < 256) direct[c] = (int16_t)k;
+            }
+        }
+        masks[(size_t)k * words + i / 64] |= 1ull << (i % 64);
+    }
+    for (w = 0; w < words; w++) S[w] = ~0ull;
+    for (i = 0; i < nb; i++) {
+        uint32_t c = b[i], k;
+        uint64_t carry = 0;
+        const uint64_t *M;
+        if (c < 256) { if (direct[c] < 0) continue; k = (uint32_t)direct[c]; }
+        else { for (k = 0; k < n_uniq && cps[k] != c; k++) {} if (k == n_uniq) continue; }
+        M = masks + (size_t)k * words;
+        for (w = 0; w < words; w++) {
+            uint64_t u = S[w] & M[w], sum = S[w] + u, sum2 = sum + carry;
+            carry = (sum < u) | (sum2 < sum);
+            S[w] = sum2 | (S[w] - u);
+        }
+    }
+    for (w = 0; w < words; w++) lcs += (uint32_t)__builtin_popcountll(~S[w]);
+    /* bits beyond the pattern length never change from 1: they do not count */
+    if (masks != stack_masks) { free(masks); free(cps); }
+    return lcs;
+}

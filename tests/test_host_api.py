@@ -193,14 +193,44 @@ GLOO_WORKER = textwrap.dedent("""
     p = pack.pack_suffix_id_sets(lens, flat, 400)
     score = lambda b, e: c_oracle.all_pairs(p, p, 0.2, l_begin=b, l_end=e)[0].astype(PAIR_DTYPE)
     weights = p.level_sizes().sum() * np.ones(p.n_items)
-    got = distributed.sharded_all_pairs(score, weights)
     want = score(0, p.n_items)
     key = lambda a: np.lexsort((a["right"], a["left"]))
+    got = distributed.sharded_all_pairs(score, weights, gather="all")   # identical on every rank
     assert sum(distributed.last_counts) == len(want), distributed.last_counts
     assert len(distributed.last_counts) == 2 and min(distributed.last_counts) > 0
     assert np.array_equal(got[key(got)], want[key(want)])
     mine = distributed.sharded_all_pairs(score, weights, gather=False)
     assert len(mine) == distributed.last_counts[dist.get_rank()]
+    # the default: rank 0 holds the complete result, the others the pairs of their own rows
+    assert distributed.default_gather() == "rank0"
+    got = distributed.sharded_all_pairs(score, weights)
+    if dist.get_rank() == 0:
+        assert np.array_equal(got[key(got)], want[key(want)])
+    else:
+        assert np.array_equal(got, mine)
+    # several comparisons through one engine call per rank + ONE count all-gather
+    from dataclasses import dataclass
+    @dataclass
+    class FakeCohort:
+        n_items: int
+        weights: np.ndarray
+    @dataclass
+    class FakeJob:
+        left: FakeCohort
+        right: FakeCohort
+        threshold: float
+        rows: tuple = None
+    class FakeEngine:
+        def run_jobs(self, jobs, **kw):
+            outs = [c_oracle.all_pairs(p, p, j.threshold, l_begin=j.rows[0], l_end=j.rows[1])[0] for j in jobs]
+            self.last_infos = [dict(count=len(o)) for o in outs]
+            return outs
+    side = FakeCohort(p.n_items, weights)
+    outs, counts = distributed.sharded_run_jobs(FakeEngine(), [FakeJob(side, side, 0.2), FakeJob(side, side, 0.5, (10, 250))])
+    assert len(counts) == 2 and len(counts[0]) == 2
+    assert counts[0][0] + counts[1][0] == len(want)
+    assert counts[0][1] + counts[1][1] == len(c_oracle.all_pairs(p, p, 0.5, l_begin=10, l_end=250)[0])
+    assert [len(o) for o in outs] == counts[dist.get_rank()]
     # a block that fails on one rank fails the call on every rank (nobody hangs in the gather)
     def broken(b, e):
         if dist.get_rank() == 1:

@@ -19,6 +19,11 @@ KNOWN = [
     ("50% der Fälle", ["50", "%", "der", "Fälle"]),
     ("COVID-19 -- schwer", ["COVID-19", "--", "schwer"]),
     ("", []),
+    # apostrophe-free contractions (Treebank CONTRACTIONS2): two tokens, also without punctuation
+    ("cannot", ["can", "not"]),
+    ("Ich wanna gehen", ["Ich", "wan", "na", "gehen"]),
+    ("gonna gotta lemme gimme", ["gon", "na", "got", "ta", "lem", "me", "gim", "me"]),
+    ("Cannot CANNOT cannots", ["Can", "not", "CAN", "NOT", "cannots"]),
 ]
 
 
@@ -45,7 +50,7 @@ def test_gen_comp_value_levels_are_suffix_token_sets():
 
 def test_incremental_gen_comp_value_equals_tokenising_every_suffix():
     rnd = random.Random(1)
-    words = ["Haus", "haus", "der", "Die", "und", "Dialyse", "x-y", "a/b", "B12", "+", "nicht", "Nieren",
+    words = ["Haus", "haus", "der", "Die", "und", "Dialyse", "x-y", "a/b", "B12", "+", "nicht", "Nieren", "cannot", "wanna",
              "über", "ÄRZTE", "1.5", "z.B.", "(ja)", "nein?", "--", "a--b", "", "ist"]
     text = lambda: " ".join(rnd.choice(words) for _ in range(rnd.randint(0, 6)))  # noqa: E731
     taken = 0
