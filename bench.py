@@ -3,20 +3,27 @@
 bench.py — the reference's headline metric on B200: item pair-scores/sec (scored + thresholded).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+                    [--secondary none|NAME,NAME] [--quick]
 
 One "step" is one pass of the comparison hot path over one batch of synthetic cohorts:
 the workload `tokenids50k` (BASELINE.json configs[1]) scores HAP x POP, HAP x SUEP and POP x SUEP,
 50 000 items per cohort, `intersection_vs_union` on the `TokenIds` column, score_threshold 0.1.
 A pair-score is one `score_func` evaluation that compare_terms asks for (max(K_left, K_right)
-per item pair), either computed exactly or proven to belong to a pair below the threshold.
+per item pair), either computed exactly or proven to belong to a pair below the threshold
+(`kernel_stats_per_step` says how many were computed exactly).
 
-N > 1 (launched by torchrun, one rank per GPU): every rank scores its own left row block of the
-same size against the replicated right cohort (weak scaling, no data-path collective); the only
-collective is the NCCL all-gather of the per-rank kept-pair counts.
+N > 1 (launched by torchrun, one rank per GPU) is STRONG scaling of that one job through the
+product's multi-GPU path (gpu/distributed.py:sharded_run_jobs): every rank holds the same cohorts,
+scores its own left row block (balanced by level sizes) of every comparison against the replicated
+right cohort, and the ranks all-gather their kept-pair counts (NCCL) inside every step.  Records
+stay sharded: each rank's go to its own pinned host arena.
 
-`--impl reference` times the CPU restatement of the reference's own Python pair loop
-(oracle/reference_port.py, all host cores through multiprocessing) on a bounded sample of the
-same workload; the reference itself is Python and /root/reference does not exist on the GPU box.
+With the default workload the line also carries `secondary`: BASELINE configs[4] (`term1m`,
+1M x 1M Term items) and configs[2] (`fuzzy200k`), sharded the same way, a few steps each.
+
+`--impl reference` times the UNMODIFIED reference's own `gen_comparable` (oracle/_ref, a copy of
+/root/reference made by oracle/make_ref.py; nltk / rapidfuzz shimmed) on all host cores, on a
+bounded sample of the same workload; without oracle/_ref it falls back to the oracle port.
 """
 from __future__ import annotations
 
@@ -75,6 +82,7 @@ WORKLOADS = {
 # workload construction (host, outside every timed region)
 # ------------------------------------------------------------------------------------------
 BUILD_INFO: dict = {}   # host_pack_s: seconds the numpy packer took for the workload's cohorts
+REF_POOL = 4000         # items per side the CPU reference arm may draw its sample from
 
 
 def build_tokenids(n: int, rank: int):
@@ -141,10 +149,13 @@ def build_fuzzyterm(n: int, rank: int):
                     pos += int(q)
             items.append([sorted({w for part in parts[-j:] for w in part}, key=lambda w: (w.casefold(), w))
                           for j in range(1, len(parts) + 1)])
+            if i < REF_POOL:   # the Term value itself, for the reference arm
+                raw.setdefault(name + "__terms", []).append([" ".join(part) for part in parts])
         levels[name] = items
     pl, pr = pack.pack_strings(pack.fuzzy_level_strings(levels["left"]),
                                pack.fuzzy_level_strings(levels["right"]))
-    return {"left": pl, "right": pr}, levels, [("left", "right")]
+    return {"left": pl, "right": pr}, {**levels, **{k: v for k, v in raw.items() if k.endswith("__terms")}}, \
+        [("left", "right")]
 
 
 def build_variable(n: int, rank: int):
@@ -158,6 +169,7 @@ def build_variable(n: int, rank: int):
         names = [f"{'gec_' if rng.random() < 0.2 else ''}{name[0]}{int(rng.integers(0, 4))}_v{int(rng.integers(0, 3 * n)):07d}"
                  for _ in range(n)]
         levels[name] = [gen_comp_value(v) for v in names]
+        levels[name + "__names"] = names[:REF_POOL]
     pl, pr = pack.pack_sets(levels["left"], levels["right"])
     return {"left": pl, "right": pr}, levels, [("left", "right")]
 
@@ -280,7 +292,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------
-# CPU reference arm (oracle port of the reference's Python pair loop)
+# CPU arms: the reference itself (oracle/_ref through oracle/ref_arm.py) and the oracle port
 # ------------------------------------------------------------------------------------------
 def _levels_from_ids(lens, flat, begin, end):
     """String level lists of items begin:end, exactly what gen_comp_value yields for TokenIds."""
@@ -316,15 +328,11 @@ def _cpu_block(args):
     return len(kept), evals, time.perf_counter() - t0
 
 
-def cpu_reference(workload: dict, raw, pairs, seconds: float, procs: int, packs=None):
-    """Times the CPU restatement of the reference's pair loop on left row blocks of the first
-    comparison until about `seconds` of wall time are used.  Returns (pair-scores/s, sample).
-
-    intersection_vs_union: oracle/reference_port.all_pairs — the reference's own Python loop
-    (compare_terms + set arithmetic per pair), `procs` processes.
-    fuzzy_match: the reference calls rapidfuzz's C++ QRatio from that Python loop; rapidfuzz is not
-    installable here, so the C restatement (oracle/nsm_oracle.c, textbook LCS) stands in for it,
-    `procs` OpenMP threads — a pure-Python LCS would understate the reference by ~1000x."""
+def cpu_port(workload: dict, raw, pairs, seconds: float, procs: int, packs=None):
+    """The CPU restatement (oracle/) of the pair loop on left row blocks of the first comparison
+    for about `seconds` of wall time.  Returns (pair-scores/s, sample).  intersection_vs_union:
+    oracle/reference_port.all_pairs (Python, `procs` processes); fuzzy_match: oracle/nsm_oracle.c
+    (C, LCS by dynamic programming, `procs` OpenMP threads)."""
     import multiprocessing as mp
 
     a, b = pairs[0]
@@ -379,31 +387,134 @@ def cpu_reference(workload: dict, raw, pairs, seconds: float, procs: int, packs=
     return done_evals / wall, sample
 
 
-def run_reference_arm(args, rank: int):
+def reference_job(workload: dict, raw, pairs) -> dict:
+    """The first comparison of the workload as frames the reference's own code takes
+    (oracle/ref_arm.py): a pool of left rows (cut into blocks there) and 1000 right rows, the
+    first rows of the same seeded cohorts the GPU arm scores."""
+    a, b = pairs[0]
+    kind, thr = workload["kind"], workload["thr"]
+    n_right = 1000
+
+    def frame(name, n, column, values, terms=None):
+        return {"Identifier": [f"{name}#{i:07d}" for i in range(n)], "Sheet": ["s"] * n,
+                "Variable": [f"{name}_v{i:07d}" for i in range(n)],
+                "Term": terms if terms is not None else [["q"]] * n, **({column: values} if column != "Term" else {})}
+
+    if kind == "tokenids":
+        def ids(name, n):
+            lens, flat = raw[name]
+            n = min(n, len(lens))
+            starts = np.concatenate([[0], np.cumsum(lens[:n])])
+            return [[f"D{int(v):06d}" for v in flat[starts[i]:starts[i + 1]]] for i in range(n)], lens[:n]
+        (lv, kl), (rv, kr) = ids(a, REF_POOL), ids(b, n_right)
+        left, right = frame(a, len(lv), "TokenIds", lv), frame(b, len(rv), "TokenIds", rv)
+        column, mode, func = "TokenIds", "gen_comparable", "intersection_vs_union"
+    elif kind == "term":
+        def terms(name, n):
+            part_lens, flat = raw[name]
+            n = min(n, len(part_lens))
+            starts = np.concatenate([[0], np.cumsum(part_lens.sum(axis=1))])
+            out = []
+            for i in range(n):
+                pos, parts = int(starts[i]), []
+                for q in part_lens[i]:
+                    if q:
+                        parts.append(" ".join(f"w{int(v)}" for v in flat[pos:pos + q]))
+                        pos += int(q)
+                out.append(parts)
+            return out, (part_lens[:n] > 0).sum(axis=1)
+        (lv, kl), (rv, kr) = terms(a, REF_POOL), terms(b, n_right)
+        left, right = frame(a, len(lv), "Term", None, lv), frame(b, len(rv), "Term", None, rv)
+        column, mode, func = "Term", "gen_comparable", "intersection_vs_union"
+    elif kind == "variable":
+        lv, rv = raw[a + "__names"][:REF_POOL], raw[b + "__names"][:n_right]
+        kl, kr = np.array([len(v) for v in lv]), np.array([len(v) for v in rv])
+        left, right = frame(a, len(lv), "Variable", lv), frame(b, len(rv), "Variable", rv)
+        column, mode, func = "Variable", "gen_comparable", "intersection_vs_union"
+    elif kind == "fuzzyterm":
+        lv, rv = raw[a + "__terms"][:REF_POOL], raw[b + "__terms"][:n_right]
+        kl, kr = np.array([len(v) for v in lv]), np.array([len(v) for v in rv])
+        left, right = frame(a, len(lv), "Term", None, lv), frame(b, len(rv), "Term", None, rv)
+        column, mode, func = "Term", "gen_comparable", "fuzzy_match"
+    else:   # flat strings: the reference's flat use of fuzzy_match is np.vectorize (mesh.py:209)
+        lv, rv = [v[0] for v in raw[a][:REF_POOL]], [v[0] for v in raw[b][:n_right]]
+        kl, kr = np.ones(len(lv), dtype=np.int64), np.ones(len(rv), dtype=np.int64)
+        left, right = frame(a, len(lv), "Question", lv), frame(b, len(rv), "Question", rv)
+        column, mode, func = "Question", "vectorize", "fuzzy_match"
+    evals_per_row = np.maximum.outer(np.asarray(kl), np.asarray(kr)).sum(axis=1)
+    rows_per_block = 50 if mode == "gen_comparable" else 10
+    return {"mode": mode, "left": left, "right": right, "rows_per_block": rows_per_block,
+            "evals_per_row": [float(v) for v in evals_per_row],
+            "kwargs": dict(score_func=func, compare_column=column, score_threshold=thr,
+                           left_name=a, right_name=b),
+            "what": ("ComparableData.gen_comparable (comparable_data.py:133-246)" if mode == "gen_comparable"
+                     else "np.vectorize(fuzzy_match) (terminology/mesh.py:209)")}
+
+
+def cpu_reference(workload: dict, raw, pairs, seconds: float, procs: int, packs=None) -> dict:
+    """`cpu_baseline` object: the reference's own code when oracle/_ref travelled with the
+    snapshot (kind "reference"), else the oracle port (kind "port")."""
+    from oracle import ref_arm
+
+    if ref_arm.available():
+        job = reference_job(workload, raw, pairs)
+        res = ref_arm.run(job, procs, seconds)
+        fuzzy = workload["kind"].startswith("fuzzy")
+        sample = (f"{res['blocks']} blocks of {job['rows_per_block']} x {len(job['right']['Identifier'])} items of "
+                  f"{pairs[0][0]} x {pairs[0][1]} ({res['pairs']} item pairs, {res['evals']:.0f} pair-scores) through the "
+                  f"unmodified reference's {job['what']} from oracle/_ref (manifest {ref_arm.manifest_digest()}), "
+                  f"{procs} process(es), {res['wall_s']:.1f} s inside the reference's calls; nltk"
+                  + (", rapidfuzz (QRatio restated, LCS in C)" if fuzzy else "") + " shimmed (absent from the image)")
+        return {"value": res["evals_per_s"], "unit": UNIT, "cores": procs, "kind": "reference",
+                "sample": sample, "item_pairs_per_s": res["pairs_per_s"]}
+    value, sample = cpu_port(workload, raw, pairs, seconds, procs, packs)
+    return {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
+            "sample": sample + " (oracle/_ref missing: run oracle/make_ref.py in the build container)"}
+
+
+def workload_config(name: str, wl: dict, packs, pairs, world: int) -> dict:
+    """`config` of the JSON line; identical keys and values in both arms."""
+    counts = [schedule_counts(packs[a], packs[b]) for a, b in pairs]
+    return {"workload": name, "desc": wl["desc"],
+            "comparisons_per_step": len(pairs),
+            "item_pairs_per_step": int(sum(packs[a].n_items * packs[b].n_items for a, b in pairs)),
+            "pair_scores_per_step": float(sum(c[0] for c in counts)),
+            "threshold": wl["thr"],
+            "partitioning": ("one GPU" if world == 1 else
+                             f"left row blocks over {world} GPUs, right cohort replicated (strong scaling)")}
+
+
+def dtype_of(wl: dict) -> str:
+    return "int32+f64" if not wl["kind"].startswith("fuzzy") else "u64+f64"
+
+
+def run_reference_arm(args, rank: int, world: int):
     if rank != 0:
         return
     wl = WORKLOADS[args.workload]
     procs = os.cpu_count() or 1
-    small = {**wl, "n": min(wl["n"], 20000), "n_right": min(wl.get("n_right", wl["n"]), 20000)}
-    packs, raw, pairs = build_workload(small, 0)
+    packs, raw, pairs = build_workload(wl, 0)
     per_step = max(5.0, min(20.0, 90.0 / max(1, args.steps + args.warmup)))
-    vals = []
-    sample = ""
+    vals, base, walls = [], None, []
     for i in range(args.warmup + args.steps):
-        v, sample = cpu_reference(wl, raw, pairs, per_step, procs, packs)
+        t0 = time.perf_counter()
+        base = cpu_reference(wl, raw, pairs, per_step, procs, packs)
         if i >= args.warmup:
-            vals.append(v)
+            vals.append(base["value"])
+            walls.append(time.perf_counter() - t0)
     value = float(np.mean(vals))
+    base["value"] = value
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "int32+f64" if not wl["kind"].startswith("fuzzy") else "u64+f64", "data": "synthetic",
-        "config": {"workload": args.workload, "desc": wl["desc"]},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
-                         "sample": sample},
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(walls)) * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": dtype_of(wl), "data": "synthetic",
+        "config": workload_config(args.workload, wl, packs, pairs, world),
+        "cpu_baseline": base,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "note": "each step is a bounded sample of the workload (see cpu_baseline.sample); "
+                "ms_per_step is the wall time of one sample, child start-up included",
     }
     print(json.dumps(line), flush=True)
 
@@ -411,6 +522,228 @@ def run_reference_arm(args, rank: int):
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
+class Prepared:
+    """One workload on this rank: host packs, pinned inputs, device cohorts, the step functions."""
+
+    def __init__(self, name: str, eng, world: int):
+        import torch
+
+        from napkon_string_matching.gpu.engine import Job
+
+        self.name, self.wl, self.eng, self.world = name, WORKLOADS[name], eng, world
+        wl = self.wl
+        BUILD_INFO.clear()
+        self.packs, self.raw, self.pairs = build_workload(wl, 0)   # the same problem on every rank
+        self.host_pack_s = BUILD_INFO.get("host_pack_s", 0.0)
+        self.flat, self.thr = wl["kind"] == "fuzzy", wl["thr"]
+        self.config = workload_config(name, wl, self.packs, self.pairs, world)
+        counts = [schedule_counts(self.packs[a], self.packs[b]) for a, b in self.pairs]
+        self.evals_step = sum(c[0] for c in counts)
+        self.ops_step = sum(c[1] for c in counts)
+        self.in_bytes = sum(p.nbytes() for p in self.packs.values())
+        self.pinned = {k: eng.pin(p) for k, p in self.packs.items()}
+        self.dev = {k: eng.upload(p, self.pinned[k]) for k, p in self.packs.items()}
+        torch.cuda.synchronize()
+        self.Job = Job
+        # Token-set workloads go end to end from the host's token codes: H2D of the raw code CSR,
+        # device-side packing (csrc/pack.cu; the frequency ranking included where the workload
+        # ranks), the comparison kernels, D2H of the kept records.  Strings start from host packs.
+        self.raw_sets, self.pack_info, self.e2e_from = None, None, "host packs (numpy)"
+        self.in_bytes_e2e = self.in_bytes
+        if wl["kind"] in ("tokenids", "term"):
+            from napkon_string_matching.gpu import device_pack as dp
+
+            make = dp.raw_from_id_lists if wl["kind"] == "tokenids" else dp.raw_from_parts
+            self.names = list(self.packs)
+            self.raw_sets = [make(*self.raw[k]).pin() for k in self.names]
+            self.n_vocab, self.rank_mode = (30000, None) if wl["kind"] == "tokenids" else (20000, "frequency")
+            self.e2e_from = "token codes (packed on the device)"
+            self.in_bytes_e2e = sum(r.nbytes() for r in self.raw_sets) + (4 * self.n_vocab if self.rank_mode else 0)
+            best = float("inf")
+            for _ in range(3):
+                torch.cuda.synchronize()
+                t_pack = time.perf_counter()
+                eng.device_packer.pack(self.raw_sets, self.n_vocab, rank=self.rank_mode)
+                torch.cuda.synchronize()
+                best = min(best, time.perf_counter() - t_pack)
+            self.pack_info = {"device_ms": best * 1e3, "host_numpy_ms": self.host_pack_s * 1e3,
+                              "what": "all cohorts of the step, token codes -> packed arrays in HBM"}
+
+    def jobs(self, dev):
+        return [self.Job(dev[a], dev[b], self.thr, flat=self.flat) for a, b in self.pairs]
+
+    def step_resident(self):
+        """Inputs resident in HBM, records left on the device; the count all-gather included."""
+        from napkon_string_matching.gpu import distributed
+
+        _, counts = distributed.sharded_run_jobs(self.eng, self.jobs(self.dev), to_host=False)
+        return counts
+
+    def step_e2e(self):
+        """The call a user makes: pinned host inputs -> this rank's records in pinned host memory."""
+        from napkon_string_matching.gpu import distributed
+
+        if self.raw_sets is not None:
+            d = dict(zip(self.names, self.eng.device_packer.pack(self.raw_sets, self.n_vocab, rank=self.rank_mode)))
+        else:
+            d = {k: self.eng.upload(p, self.pinned[k]) for k, p in self.packs.items()}
+        outs, counts = distributed.sharded_run_jobs(self.eng, self.jobs(d), to_host=True, decode=False)
+        self.last_records = outs
+        return counts, sum(i["d2h_bytes"] for i in self.eng.last_infos), \
+            sum(i["packets"] for i in self.eng.last_infos), sum(i["reruns"] for i in self.eng.last_infos)
+
+
+def measure(prep: Prepared, steps: int, warmup: int, rank: int, world: int, int_peaks: dict, hbm_peak: float,
+            separate_resident: bool, sampler=None) -> dict:
+    """Times `steps` steps of one workload.  separate_resident: the device-resident steps (`value`)
+    are timed by themselves, then the end-to-end steps; otherwise `value` comes from the CUDA
+    events around the kernel launches inside the end-to-end steps (secondary workloads)."""
+    import torch
+    import torch.distributed as dist
+
+    eng = prep.eng
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def timed(step_fn, flush: bool):
+        """K steps, each bracketed by CUDA events on the launching stream; returns (ms, last)."""
+        evs, last = [], None
+        for _ in range(steps):
+            if flush:
+                flush_buf.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            last = step_fn()
+            b.record(stream)
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs), last
+
+    def max_over_ranks(*vals):
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    def sum_over_ranks(*vals):
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(v) for v in t]
+
+    clocks = None
+    ms = kernel_ms = kernel_launches = launches = None
+    stats = None
+    if separate_resident:
+        for _ in range(warmup):
+            counts = prep.step_resident()
+        kept_mine = counts[rank]
+        # L2 (126 MB) between timed steps: a step that writes more than 2x L2 of records flushes it
+        # by itself; otherwise a 256 MB buffer is overwritten before every step, outside the events
+        self_flushing = 16 * sum(kept_mine) > 2 * (126 << 20)
+        if sampler is not None:
+            sampler.start()
+            time.sleep(0.3)
+        barrier()
+        launches0 = eng.launches
+        eng.time_kernels, eng.kernel_ms, eng.kernel_launches_timed = True, 0.0, 0
+        t0 = time.time()
+        ms, counts = timed(prep.step_resident, not self_flushing)
+        barrier()
+        t1 = time.time()
+        eng.time_kernels = False
+        launches = eng.launches - launches0
+        kernel_ms, kernel_launches = eng.kernel_ms, eng.kernel_launches_timed
+        stats = {k: sum(i["stats"][k] for i in eng.last_infos) for k in eng.last_infos[0]["stats"]}
+        if sampler is not None:
+            clocks = sampler.stop(t0, t1)
+    # ---- end to end ---------------------------------------------------------------------
+    for _ in range(warmup):
+        counts_e2e, d2h, packets, reruns = prep.step_e2e()
+    self_flushing = d2h > 2 * (126 << 20)
+    if not separate_resident and sampler is not None:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    launches0 = eng.launches
+    eng.time_kernels, eng.kernel_ms, eng.kernel_launches_timed = True, 0.0, 0
+    t0 = time.time()
+    ms_e2e, (counts_e2e, d2h, packets, reruns) = timed(prep.step_e2e, not self_flushing)
+    barrier()
+    t1 = time.time()
+    eng.time_kernels = False
+    e2e_kernel_ms, e2e_kernel_launches, e2e_launches = eng.kernel_ms, eng.kernel_launches_timed, eng.launches - launches0
+    if not separate_resident:
+        ms, kernel_ms, kernel_launches, launches = e2e_kernel_ms, e2e_kernel_ms, e2e_kernel_launches, e2e_launches
+        stats = {k: sum(i["stats"][k] for i in eng.last_infos) for k in eng.last_infos[0]["stats"]}
+        counts = counts_e2e
+        if sampler is not None:
+            clocks = sampler.stop(t0, t1)
+    else:
+        assert counts_e2e == counts, (counts_e2e, counts)
+
+    ms, ms_e2e = max_over_ranks(ms, ms_e2e)
+    kernel_ms_sum, launches_sum, kernel_launches_sum, d2h_sum, packets_sum, reruns_sum, stat_sums = None, None, None, None, None, None, None
+    names = list(stats)
+    sums = sum_over_ranks(kernel_ms, launches, kernel_launches, d2h, packets, reruns, *[stats[k] for k in names])
+    kernel_ms_sum, launches_sum, kernel_launches_sum, d2h_sum, packets_sum, reruns_sum = sums[:6]
+    stats = dict(zip(names, (int(v) for v in sums[6:])))
+    kept_jobs = [sum(c[j] for c in counts) for j in range(len(prep.pairs))]
+    kept = sum(kept_jobs)
+
+    sec_step = ms * 1e-3 / steps
+    value = prep.evals_step / sec_step
+    peak_ops = max(int_peaks["lop3"], int_peaks["iadd3"])
+    # the roofline is per kernel launch and per GPU: algorithmic ops of the step / the kernel time
+    # all GPUs spent on it (CUDA events around every launch on the launching stream)
+    kernel_sec_step = kernel_ms_sum * 1e-3 / steps
+    achieved = prep.ops_step / kernel_sec_step
+    alg_bytes = prep.in_bytes * world + 16 * kept
+    out = {
+        "value": value, "ms_per_step": ms / steps,
+        "config": {**prep.config, "kept_pairs_per_step": kept_jobs,
+                   "kept_pairs_per_rank": [sum(c) for c in counts],
+                   "value_timing": ("device-resident steps timed by themselves (records stay in HBM)"
+                                    if separate_resident else
+                                    "sum of the CUDA-event times of the kernel launches inside the end-to-end steps"),
+                   "l2": ("flushed by the step itself: each step writes %.0f MB of records, %.0fx the 126 MB L2"
+                          % (16e-6 * kept / world, 16 * kept / world / (126 << 20))) if self_flushing
+                   else "a 256 MB buffer is overwritten before every timed step (outside the events)"},
+        "item_pairs_per_s": prep.config["item_pairs_per_step"] / sec_step,
+        "roofline": {"bound": "int32_alu", "achieved": achieved / 1e12, "peak": peak_ops / 1e12,
+                     "unit": "Tiop/s", "frac": achieved / peak_ops,
+                     "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(prep.name) if world == 1 else None,
+                     "peak_source": "nsm_microbench measured in this run (LOP3/IADD3 stream), per GPU",
+                     "alg_ops_per_step": prep.ops_step,
+                     "launches_per_step": kernel_launches_sum / steps,
+                     "kernel_ms_per_launch": kernel_ms_sum / max(1, kernel_launches_sum),
+                     "kernel_share_of_step": kernel_ms_sum / world / ms if separate_resident else None,
+                     "exactly_scored_share": stats["level_evals"] / max(1.0, prep.evals_step)},
+        "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / kernel_sec_step / 1e9, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": alg_bytes / kernel_sec_step / 1e9 / hbm_peak},
+        "kernel_stats_per_step": stats,
+        "e2e": {"value": prep.evals_step / (ms_e2e * 1e-3 / steps), "unit": UNIT,
+                "ms_per_step": ms_e2e / steps, "h2d_bytes_per_step": prep.in_bytes_e2e * world,
+                "d2h_bytes_per_step": int(d2h_sum), "from": prep.e2e_from,
+                "to": "records in each rank's pinned host arena, in the C ABI's wire format",
+                "record_format": ("nsm_packet_t: %.2f bytes per kept pair (%d packets)"
+                                  % (d2h_sum / max(1, kept), packets_sum)) if packets_sum else
+                                 "nsm_pair_t: 16 bytes per kept pair",
+                "kernel_ms_per_step": e2e_kernel_ms / steps, "overflow_reruns_per_step": reruns_sum / steps,
+                "collective": "NCCL all-gather of the kept-pair counts, every step" if world > 1 else None},
+        "pack": prep.pack_info,
+        "gpu_launches": int(launches_sum),
+        "clocks": clocks,
+    }
+    return out
+
+
 def run_ours(args, rank: int, world: int, local_rank: int):
     import torch
     import torch.distributed as dist
@@ -425,189 +758,72 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
         bound_cpus = affinity.bind_to_gpu(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    wl = WORKLOADS[args.workload]
-    packs, raw, pairs = build_workload(wl, rank)
-    host_pack_s = BUILD_INFO.get("host_pack_s", 0.0)
-    flat = wl["kind"] == "fuzzy"
-    thr = wl["thr"]
-
     eng = Engine()
-    pinned = {k: eng.pin(p) for k, p in packs.items()}
-    counts = [schedule_counts(packs[a], packs[b]) for a, b in pairs]
-    evals_step = sum(c[0] for c in counts)
-    ops_step = sum(c[1] for c in counts)
-    item_pairs_step = sum(packs[a].n_items * packs[b].n_items for a, b in pairs)
-    in_bytes = sum(p.nbytes() for p in packs.values())
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except OSError:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    int_peaks = {name: eng.microbench(kind) for kind, name in
+                 enumerate(("lop3", "iadd3", "popc", "lcs_step_u64"))}
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    wl = WORKLOADS[args.workload]
+    prep = Prepared(args.workload, eng, world)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    warmup = max(3, args.warmup)
+    res = measure(prep, args.steps, warmup, rank, world, int_peaks, hbm_peak, True, sampler)
 
-    stream = torch.cuda.current_stream()
-    dev = {k: eng.upload(p, pinned[k]) for k, p in packs.items()}
-    torch.cuda.synchronize()
-
-    from napkon_string_matching.gpu.engine import Job
-
-    def step_resident():
-        eng.run_jobs([Job(dev[a], dev[b], thr, flat=flat) for a, b in pairs], to_host=False)
-        return sum(i["count"] for i in eng.last_infos)
-
-    # Token-set workloads go end to end from the host's token codes: H2D of the raw code CSR,
-    # device-side packing (csrc/pack.cu; the frequency ranking included where the workload ranks),
-    # the comparison kernels, D2H of the kept records.  String workloads start from host packs.
-    raw_sets, pack_info, e2e_from = None, None, "host packs (numpy)"
-    if wl["kind"] in ("tokenids", "term"):
-        from napkon_string_matching.gpu import device_pack as dp
-
-        make = dp.raw_from_id_lists if wl["kind"] == "tokenids" else dp.raw_from_parts
-        names = list(packs)
-        raw_sets = [make(*raw[k]).pin() for k in names]
-        n_vocab, rank_mode = (30000, None) if wl["kind"] == "tokenids" else (20000, "frequency")
-        e2e_from = "token codes (packed on the device)"
-        in_bytes_e2e = sum(r.nbytes() for r in raw_sets) + (4 * n_vocab if rank_mode else 0)
-        best = float("inf")
-        for _ in range(3):
-            torch.cuda.synchronize()
-            t_pack = time.perf_counter()
-            eng.device_packer.pack(raw_sets, n_vocab, rank=rank_mode)
-            torch.cuda.synchronize()
-            best = min(best, time.perf_counter() - t_pack)
-        pack_info = {"device_ms": best * 1e3, "host_numpy_ms": host_pack_s * 1e3,
-                     "what": "all cohorts of the step, token codes -> packed arrays in HBM"}
+    decode = None
+    if rank == 0 and not args.quick:
+        # host side of the packet format: ms to expand one comparison's records of the last step
+        rec = max(prep.last_records, key=len)
+        t0 = time.perf_counter()
+        arr = rec.decode(copy=False)
+        decode = {"records": int(len(arr)), "ms": (time.perf_counter() - t0) * 1e3,
+                  "what": "numpy expansion of one comparison's records to (left, right, score) arrays; not in e2e"}
+        del arr
+    if args.quick:   # kernel experiments: no CPU baseline leg (not a bench line to report)
+        cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": "skipped (--quick)"}
+    elif world > 1 or rank != 0:  # the CPU baseline is timed at N = 1 only
+        cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "timed at N=1 only"}
     else:
-        in_bytes_e2e = in_bytes
+        cpu = cpu_reference(wl, prep.raw, prep.pairs, 12.0, 1, prep.packs)
+        port_value, port_sample = cpu_port(wl, prep.raw, prep.pairs, 5.0, 1, prep.packs)
+        cpu["port"] = {"value": port_value, "sample": port_sample}
 
-    def step_e2e():
-        if raw_sets is not None:
-            d = dict(zip(names, eng.device_packer.pack(raw_sets, n_vocab, rank=rank_mode)))
-        else:
-            d = {k: eng.upload(p, pinned[k]) for k, p in packs.items()}
-        outs = eng.run_jobs([Job(d[a], d[b], thr, flat=flat) for a, b in pairs], to_host=True,
-                            copy=False)
-        return sum(len(o) for o in outs), sum(i["d2h_bytes"] for i in eng.last_infos)
-
-    # ---- kernel-resident timing (value) -------------------------------------------------
-    for _ in range(max(3, args.warmup)):
-        kept = step_resident()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
-    barrier()
-    launches0 = eng.launches
-    eng.time_kernels, eng.kernel_ms, eng.kernel_launches_timed = True, 0.0, 0
-    # L2 (126 MB) between timed steps: a step that writes more than 2x L2 of records flushes it by
-    # itself; otherwise a 256 MB buffer is overwritten before every step, outside the timed events
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    self_flushing = 16 * kept > 2 * (126 << 20)
-
-    def timed(step_fn):
-        """K steps, each bracketed by CUDA events on the launching stream; returns (ms, last)."""
-        pairs_ev, last = [], None
-        for _ in range(args.steps):
-            if not self_flushing:
-                flush_buf.zero_()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            last = step_fn()
-            b.record(stream)
-            pairs_ev.append((a, b))
-        torch.cuda.synchronize()
-        return sum(a.elapsed_time(b) for a, b in pairs_ev), last
-
-    t0 = time.time()
-    ms, kept = timed(step_resident)
-    barrier()
-    t1 = time.time()
-    eng.time_kernels = False
-    launches = eng.launches - launches0
-    kernel_ms, kernel_launches = eng.kernel_ms, eng.kernel_launches_timed
-    stats = {k: sum(i["stats"][k] for i in eng.last_infos) for k in eng.last_infos[0]["stats"]}
-    clocks = sampler.stop(t0, t1) if rank == 0 else None
-
-    # ---- end-to-end timing (host packs -> host records) ---------------------------------
-    for _ in range(max(3, args.warmup)):
-        step_e2e()
-    barrier()
-    ms_e2e, (kept_e2e, d2h) = timed(step_e2e)
-    barrier()
-    assert kept_e2e == kept, (kept_e2e, kept)
-
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([kept], dtype=torch.int64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        gathered = [torch.zeros_like(cnt) for _ in range(world)]
-        dist.all_gather(gathered, cnt)  # the path's one collective: kept-pair counts
-        kept_all = [int(g.item()) for g in gathered]
-    else:
-        kept_all = [kept]
-    ms, ms_e2e = float(t[0]), float(t[1])
+    secondary = {}
+    names = [] if args.secondary == "none" else \
+        (["term1m", "fuzzy200k"] if args.secondary == "default" and args.workload == "tokenids50k"
+         else [n for n in args.secondary.split(",") if n in WORKLOADS and args.secondary != "default"])
+    del prep
+    torch.cuda.empty_cache()
+    for name in names:
+        eng._buffers.clear()
+        torch.cuda.empty_cache()
+        p2 = Prepared(name, eng, world)
+        r2 = measure(p2, max(1, min(3, args.steps)), 1, rank, world, int_peaks, hbm_peak, False, None)
+        r2["dtype"] = dtype_of(WORKLOADS[name])
+        secondary[name] = r2
+        del p2
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
-        except OSError:
-            pass
-        int_peaks = {name: eng.microbench(kind) for kind, name in
-                     enumerate(("lop3", "iadd3", "popc", "lcs_step_u64"))}
-        peak_ops = max(int_peaks["lop3"], int_peaks["iadd3"])
-        sec_step = ms * 1e-3 / args.steps
-        value = evals_step * world / sec_step
-        # the roofline is per kernel launch: algorithmic ops of one step / kernel time of one step
-        # (CUDA events around every launch on the launching stream)
-        kernel_sec_step = kernel_ms * 1e-3 / args.steps
-        achieved = ops_step / kernel_sec_step
-        hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        alg_bytes = in_bytes + 16 * kept
-        sec_step_hbm = kernel_sec_step
-        if args.quick:   # kernel experiments: no CPU baseline leg (not a bench line to report)
-            cpu_val, cpu_sample = None, "skipped (--quick)"
-        elif world > 1:  # the CPU baseline is timed at N = 1 only
-            cpu_val, cpu_sample = None, "timed at N=1 only"
-        else:
-            cpu_val, cpu_sample = cpu_reference(wl, raw, pairs, 12.0, 1, packs)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int32+f64" if not wl["kind"].startswith("fuzzy") else "u64+f64", "data": "synthetic",
-            "config": {"workload": args.workload, "desc": wl["desc"],
-                       "item_pairs_per_step_per_gpu": item_pairs_step,
-                       "pair_scores_per_step_per_gpu": evals_step,
-                       "kept_pairs_per_step": kept_all,
-                       "l2": ("flushed by the step itself: each step writes %.0f MB of records, %.0fx "
-                              "the 126 MB L2" % (16e-6 * kept, 16 * kept / (126 << 20))) if self_flushing
-                       else "a 256 MB buffer is overwritten before every timed step (outside the events)"},
-            "item_pairs_per_s": item_pairs_step * world / sec_step,
-            "roofline": {"bound": "int32_alu", "achieved": achieved / 1e12, "peak": peak_ops / 1e12,
-                         "unit": "Tiop/s", "frac": achieved / peak_ops,
-                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.workload),
-                         "peak_source": "nsm_microbench measured in this run (LOP3/IADD3 stream)",
-                         "alg_ops_per_step": ops_step, "launches_per_step": kernel_launches / args.steps,
-                         "kernel_ms_per_launch": kernel_ms / max(1, kernel_launches),
-                         "kernel_share_of_step": kernel_ms / ms},
-            "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / sec_step_hbm / 1e9,
-                             "peak": hbm_peak, "unit": "GB/s",
-                             "frac": alg_bytes / sec_step_hbm / 1e9 / hbm_peak,
-                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+            "metric": METRIC, "value": res.pop("value"), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": res.pop("ms_per_step"),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": dtype_of(wl), "data": "synthetic",
+            **res,
+            "roofline_hbm": {**res["roofline_hbm"], "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
             "int_peaks_tiops": {k: v / 1e12 for k, v in int_peaks.items()},
-            "kernel_stats_per_step": stats,
-            "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": 1, "kind": "port",
-                             "sample": cpu_sample},
-            "e2e": {"value": evals_step * world / (ms_e2e * 1e-3 / args.steps), "unit": UNIT,
-                    "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": in_bytes_e2e,
-                    "d2h_bytes_per_step": d2h, "from": e2e_from},
-            "pack": pack_info,
-            "gpu_launches": launches,
+            "cpu_baseline": cpu,
+            "decode": decode,
+            "secondary": secondary,
             "numa": {"rank0_bound_to_cpus": len(bound_cpus) if bound_cpus else None},
-            "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -618,6 +834,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="tokenids50k", choices=sorted(WORKLOADS))
+    ap.add_argument("--secondary", default="default",
+                    help="'default' (term1m,fuzzy200k beside the default workload), 'none', or a comma list")
     ap.add_argument("--quick", action="store_true",
                     help="skip the CPU baseline leg (kernel experiments and ncu captures only)")
     args = ap.parse_args()
@@ -625,8 +843,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference_arm(args, rank)
+        run_reference_arm(args, rank, world)
     else:
+        if args.quick and args.secondary == "default":
+            args.secondary = "none"
         run_ours(args, rank, world, local_rank)
 
 

@@ -63,6 +63,10 @@ def test_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["metric"] == bench.METRIC and line["unit"] == bench.UNIT
     assert line["value"] > 0 and line["higher_is_better"] is True and line["vs_baseline"] is None
     assert line["config"]["workload"] == "tokenids50k"
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    from oracle import ref_arm
+
+    assert line["cpu_baseline"]["kind"] == ("reference" if ref_arm.available() else "port")
+    assert line["cpu_baseline"]["cores"] >= 1 and line["scaling"] == "strong"
+    assert {"workload", "item_pairs_per_step", "pair_scores_per_step", "threshold"} <= set(line["config"])
     assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0

@@ -1,0 +1,176 @@
+"""The compact record format (include/nsm.h:nsm_packet_t).  CPU: the host decoder on hand-built
+packets.  GPU: NSM_OUT_PACKETS against NSM_OUT_PAIRS and the oracle, the probe-sized pipeline of
+the engine, and the product's multi-GPU path on real GPUs (skipped below two devices)."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+from conftest import PKG, ROOT, assert_same_triples
+from napkon_string_matching import synthetic as syn
+from napkon_string_matching.gpu import lib as nsmlib
+from napkon_string_matching.gpu import pack
+
+
+def test_decode_packets_on_hand_built_packets():
+    rng = np.random.default_rng(5)
+    n = 37
+    pk = np.zeros(n, dtype=nsmlib.PACKET_DTYPE)
+    want = []
+    for i in range(n):
+        cnt = int(rng.integers(0, nsmlib.PACKET_RECORDS + 1)) if i % 5 else nsmlib.PACKET_RECORDS
+        l0, r0 = int(rng.integers(0, 1 << 20)) * 512, int(rng.integers(0, 1 << 18)) * 128
+        pk[i]["left0"], pk[i]["right0"], pk[i]["count"] = l0, r0, cnt
+        pk[i]["score"][:] = np.nan          # unused slots hold garbage
+        pk[i]["local"][:] = 0xffff
+        for s in range(cnt):
+            li, rc, sc = int(rng.integers(0, 512)), int(rng.integers(0, 128)), float(rng.random())
+            pk[i]["local"][s] = (li << 7) | rc
+            pk[i]["score"][s] = sc
+            want.append((l0 + li, r0 + rc, sc))
+    out = nsmlib.decode_packets(pk)
+    assert out.dtype == nsmlib.PAIR_DTYPE and len(out) == len(want)
+    assert [(int(a), int(b), float(c)) for a, b, c in zip(out["left"], out["right"], out["score"])] == want
+    assert len(nsmlib.decode_packets(pk[:0])) == 0
+
+
+def _tokenid_packs(nl, nr):
+    lens, flat = syn.token_id_level_sets(nl, syn.SEED_LEFT)
+    pl = pack.pack_suffix_id_sets(lens, flat, 30000)
+    lens, flat = syn.token_id_level_sets(nr, syn.SEED_RIGHT)
+    return pl, pack.pack_suffix_id_sets(lens, flat, 30000)
+
+
+@pytest.mark.gpu
+def test_packets_equal_pairs_and_oracle(engine):
+    from oracle import c_oracle
+
+    pl, pr = _tokenid_packs(1500, 1100)          # ragged: 3 left chunks (the last partial) x 9 right blocks
+    dl, dr = engine.upload(pl), engine.upload(pr)
+    want, _ = c_oracle.all_pairs(pl, pr, 0.1)
+    old = engine.compact
+    try:
+        engine.compact = False
+        plain = engine.all_pairs(dl, dr, 0.1)
+        assert engine.last_info["packets"] == 0
+        engine.compact = True
+        packed = engine.all_pairs(dl, dr, 0.1)
+        info = engine.last_info
+        assert info["packets"] > 0 and info["count"] == len(packed)
+        # full packets except at most one per warp and unit
+        assert info["packets"] <= len(packed) // nsmlib.PACKET_RECORDS + 4 * 3 * 9
+        # a row block and an overflowing arena (exact re-run) in packet mode
+        block = engine.all_pairs(dl, dr, 0.1, rows=(300, 1301), capacity=64)
+        assert engine.last_info["reruns"] == 1
+    finally:
+        engine.compact = old
+    for got in (plain, packed):
+        assert_same_triples((got["left"], got["right"], got["score"]),
+                            (want["left"], want["right"], want["score"]))
+    sel = (want["left"] >= 300) & (want["left"] < 1301)
+    assert_same_triples((block["left"], block["right"], block["score"]),
+                        (want["left"][sel], want["right"][sel], want["score"][sel]))
+
+
+@pytest.mark.gpu
+def test_probe_sized_pipeline_has_no_reruns(engine, monkeypatch):
+    """A job large enough for the probe path: the probe block sizes the arenas of the rest (no
+    overflow re-run), dense results switch to packets, and the union is the plain result."""
+    from napkon_string_matching.gpu.engine import Engine
+
+    pl, pr = _tokenid_packs(9000, 3000)
+    dl, dr = engine.upload(pl), engine.upload(pr)
+    monkeypatch.setattr(Engine, "PIPELINE_MIN_PAIRS", 1 << 20)
+    monkeypatch.setattr(Engine, "PIPELINE_BLOCK_BYTES", 4 << 20)   # several blocks
+    old = engine.compact
+    try:
+        engine.compact = "auto"
+        piped = engine.all_pairs(dl, dr, 0.1)
+        info = dict(engine.last_info)
+        engine.compact = False
+        monkeypatch.setattr(Engine, "PIPELINE_MIN_PAIRS", 1 << 62)
+        plain = engine.all_pairs(dl, dr, 0.1)
+    finally:
+        engine.compact = old
+    assert info["reruns"] == 0 and info["blocks"] >= 3 and info["packets"] > 0
+    assert info["d2h_bytes"] < 13 * len(plain)          # < 13 bytes per kept pair on the wire
+    assert_same_triples((piped["left"], piped["right"], piped["score"]),
+                        (plain["left"], plain["right"], plain["score"]))
+    # sparse results stay in the 16-byte format
+    monkeypatch.setattr(Engine, "PIPELINE_MIN_PAIRS", 1 << 20)
+    engine.compact = "auto"
+    sparse = engine.all_pairs(dl, dr, 0.6)
+    assert engine.last_info["packets"] == 0 and engine.last_info["reruns"] == 0
+    engine.compact = old
+    want = plain[plain["score"] >= 0.6]
+    assert_same_triples((sparse["left"], sparse["right"], sparse["score"]),
+                        (want["left"], want["right"], want["score"]))
+
+
+NCCL_WORKER = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, {pkg!r}); sys.path.insert(0, {root!r})
+    import numpy as np
+    import torch, torch.distributed as dist
+    from napkon_string_matching import synthetic as syn
+    from napkon_string_matching.gpu import distributed, pack
+    from napkon_string_matching.gpu.engine import Engine, Job
+    from oracle import c_oracle
+
+    rank = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+    eng = Engine()
+    packs = []
+    for n, seed in ((5000, 11), (3000, 12), (2500, 13)):
+        lens, flat = syn.token_id_level_sets(n, seed)
+        packs.append(pack.pack_suffix_id_sets(lens, flat, 30000))
+    dev = [eng.upload(p) for p in packs]
+    pairs = [(0, 1), (0, 2), (1, 2)]
+    eng.compact = True if os.environ.get("NSM_TEST_COMPACT") == "1" else "auto"
+    outs, counts = distributed.sharded_run_jobs(eng, [Job(dev[a], dev[b], 0.1) for a, b in pairs])
+    assert len(counts) == dist.get_world_size()
+    key = lambda a: np.lexsort((a["right"], a["left"]))
+    for j, (a, b) in enumerate(pairs):
+        want, _ = c_oracle.all_pairs(packs[a], packs[b], 0.1)
+        assert sum(c[j] for c in counts) == len(want), (j, counts, len(want))
+        lo, hi = distributed.partition_rows(dev[a].weights, dist.get_world_size())[dist.get_rank()]
+        sel = (want["left"] >= lo) & (want["left"] < hi)
+        mine, w = outs[j], want[sel]
+        assert len(mine) == counts[dist.get_rank()][j] == len(w)
+        mine, w = mine[key(mine)], w[key(w)]
+        assert np.array_equal(mine["left"], w["left"]) and np.array_equal(mine["right"], w["right"])
+        assert np.array_equal(mine["score"].view(np.uint64), w["score"].view(np.uint64))
+    # the drop-in's single-comparison path: rank 0 ends up with the complete result
+    got = distributed.sharded_all_pairs(lambda b, e: eng.all_pairs(dev[0], dev[1], 0.1, rows=(b, e)), dev[0].weights)
+    if dist.get_rank() == 0:
+        want, _ = c_oracle.all_pairs(packs[0], packs[1], 0.1)
+        got, want = got[key(got)], want[key(want)]
+        assert np.array_equal(got["left"], want["left"]) and np.array_equal(got["score"].view(np.uint64), want["score"].view(np.uint64))
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.stdout.write("rank%sok" % os.environ["RANK"] + chr(10))
+""")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("compact", ["0", "1"])
+def test_sharded_run_jobs_on_real_gpus(tmp_path, compact):
+    import torch
+
+    n_dev = torch.cuda.device_count()
+    if n_dev < 2:
+        pytest.skip("needs at least two GPUs")
+    world = 2 if n_dev < 4 else 4
+    script = tmp_path / "worker.py"
+    script.write_text(NCCL_WORKER.format(pkg=str(PKG), root=str(ROOT)))
+    res = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+         "--master-addr", "127.0.0.1", "--master-port", "29581", str(script)],
+        capture_output=True, text=True, timeout=600,
+        env={**os.environ, "OMP_NUM_THREADS": "4", "NSM_TEST_COMPACT": compact})
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert res.stdout.count("ok") == world, res.stdout
