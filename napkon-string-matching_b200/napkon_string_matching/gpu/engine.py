@@ -337,7 +337,10 @@ class Engine:
             stats = [int(x) for x in words[2:2 + nsmlib.N_STATS]]
             j, rb, re_, mode = p_item["j"], p_item["rb"], p_item["re"], p_item["mode"]
             job, info = jobs[j], infos[j]
-            kept = stats[nsmlib.STAT_NAMES.index("kept")] if mode == nsmlib.OUT_PACKETS else count
+            i_kept = nsmlib.STAT_NAMES.index("kept")
+            if mode == nsmlib.OUT_PAIRS:
+                stats[i_kept] = count    # the fuzzy kernel does not keep this counter
+            kept = stats[i_kept]
             if flags & nsmlib.FLAG_OVERFLOW:
                 # `count` is exact (pairs or packets): repeat with that size, or split the block
                 info["reruns"] += 1

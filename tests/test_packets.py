@@ -63,6 +63,7 @@ def test_packets_equal_pairs_and_oracle(engine):
         # full packets except at most one per warp and unit
         assert info["packets"] <= len(packed) // nsmlib.PACKET_RECORDS + 4 * 3 * 9
         # a row block and an overflowing arena (exact re-run) in packet mode
+        engine._buffers.pop("out0", None), engine._buffers.pop("out1", None)   # arenas only grow
         block = engine.all_pairs(dl, dr, 0.1, rows=(300, 1301), capacity=64)
         assert engine.last_info["reruns"] == 1
     finally:
