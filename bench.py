@@ -589,8 +589,9 @@ class Prepared:
             d = {k: self.eng.upload(p, self.pinned[k]) for k, p in self.packs.items()}
         outs, counts = distributed.sharded_run_jobs(self.eng, self.jobs(d), to_host=True, decode=False)
         self.last_records = outs
-        return counts, sum(i["d2h_bytes"] for i in self.eng.last_infos), \
-            sum(i["packets"] for i in self.eng.last_infos), sum(i["reruns"] for i in self.eng.last_infos)
+        infos = self.eng.last_infos
+        return counts, sum(i["d2h_bytes"] for i in infos), sum(i["packets"] for i in infos), \
+            sum(i["reruns"] for i in infos), sum(i["uncoded"] for i in infos)
 
 
 def measure(prep: Prepared, steps: int, warmup: int, rank: int, world: int, int_peaks: dict, hbm_peak: float,
@@ -665,7 +666,7 @@ def measure(prep: Prepared, steps: int, warmup: int, rank: int, world: int, int_
             clocks = sampler.stop(t0, t1)
     # ---- end to end ---------------------------------------------------------------------
     for _ in range(warmup):
-        counts_e2e, d2h, packets, reruns = prep.step_e2e()
+        counts_e2e, d2h, packets, reruns, uncoded = prep.step_e2e()
     self_flushing = d2h > 2 * (126 << 20)
     if not separate_resident and sampler is not None:
         sampler.start()
@@ -674,7 +675,7 @@ def measure(prep: Prepared, steps: int, warmup: int, rank: int, world: int, int_
     launches0 = eng.launches
     eng.time_kernels, eng.kernel_ms, eng.kernel_launches_timed = True, 0.0, 0
     t0 = time.time()
-    ms_e2e, (counts_e2e, d2h, packets, reruns) = timed(prep.step_e2e, not self_flushing)
+    ms_e2e, (counts_e2e, d2h, packets, reruns, uncoded) = timed(prep.step_e2e, not self_flushing)
     barrier()
     t1 = time.time()
     eng.time_kernels = False
@@ -689,11 +690,11 @@ def measure(prep: Prepared, steps: int, warmup: int, rank: int, world: int, int_
         assert counts_e2e == counts, (counts_e2e, counts)
 
     ms, ms_e2e = max_over_ranks(ms, ms_e2e)
-    kernel_ms_sum, launches_sum, kernel_launches_sum, d2h_sum, packets_sum, reruns_sum, stat_sums = None, None, None, None, None, None, None
     names = list(stats)
-    sums = sum_over_ranks(kernel_ms, launches, kernel_launches, d2h, packets, reruns, *[stats[k] for k in names])
-    kernel_ms_sum, launches_sum, kernel_launches_sum, d2h_sum, packets_sum, reruns_sum = sums[:6]
-    stats = dict(zip(names, (int(v) for v in sums[6:])))
+    sums = sum_over_ranks(kernel_ms, launches, kernel_launches, d2h, packets, reruns, uncoded,
+                          *[stats[k] for k in names])
+    kernel_ms_sum, launches_sum, kernel_launches_sum, d2h_sum, packets_sum, reruns_sum, uncoded_sum = sums[:7]
+    stats = dict(zip(names, (int(v) for v in sums[7:])))
     kept_jobs = [sum(c[j] for c in counts) for j in range(len(prep.pairs))]
     kept = sum(kept_jobs)
 
@@ -732,8 +733,9 @@ def measure(prep: Prepared, steps: int, warmup: int, rank: int, world: int, int_
                 "ms_per_step": ms_e2e / steps, "h2d_bytes_per_step": prep.in_bytes_e2e * world,
                 "d2h_bytes_per_step": int(d2h_sum), "from": prep.e2e_from,
                 "to": "records in each rank's pinned host arena, in the C ABI's wire format",
-                "record_format": ("nsm_packet_t: %.2f bytes per kept pair (%d packets)"
-                                  % (d2h_sum / max(1, kept), packets_sum)) if packets_sum else
+                "record_format": ("packets (include/nsm.h NSM_OUT_CODED / NSM_OUT_PACKETS): %.2f bytes per kept "
+                                  "pair (%d packets, %d pairs uncoded)"
+                                  % (d2h_sum / max(1, kept), packets_sum, uncoded_sum)) if packets_sum else
                                  "nsm_pair_t: 16 bytes per kept pair",
                 "kernel_ms_per_step": e2e_kernel_ms / steps, "overflow_reruns_per_step": reruns_sum / steps,
                 "collective": "NCCL all-gather of the kept-pair counts, every step" if world > 1 else None},

@@ -61,7 +61,17 @@ typedef struct nsm_pair {
                              ~10.4 bytes per kept pair for results that are bound by the
                              device->host link.  The kept pairs of one packet lie in one
                              512 x 128 block of the cross product. */
+#define NSM_OUT_CODED 2   /* out_pairs is nsm_cpacket_t[out_capacity] (nsm_jaccard_allpairs only):
+                             4.3 bytes per kept pair.  The float64 score of a pair is replaced by a
+                             16-bit code: its slot in the score dictionary out_dict, an open-addressing
+                             hash table over the score's bit pattern that the kernel fills first come,
+                             first served (dense results hold few distinct scores: 99 % of the 1.4e8
+                             kept pairs of a 50k x 50k TokenIds comparison share < 65536 values).  A
+                             pair whose score finds no slot goes to out_exc as a plain nsm_pair_t. */
 #define NSM_PACKET_RECORDS 48
+#define NSM_CPACKET_RECORDS 60
+#define NSM_DICT_SLOTS 65536u
+#define NSM_DICT_FREE 0xffffffffffffffffull /* a free dictionary slot (not the bits of any score) */
 
 /* Up to 48 kept pairs of the block (left0 .. left0+511) x (right0 .. right0+127):
  * pair i (i < count) is (left0 + (local[i] >> 7), right0 + (local[i] & 127), score[i]). */
@@ -73,6 +83,16 @@ typedef struct nsm_packet {
     double score[NSM_PACKET_RECORDS];
     uint16_t local[NSM_PACKET_RECORDS];
 } nsm_packet_t; /* 496 bytes */
+
+/* NSM_OUT_CODED: pair i (i < count) is (left0 + ((rec[i] & 0xffff) >> 7), right0 + (rec[i] & 127),
+ * the float64 whose bit pattern is out_dict[rec[i] >> 16]). */
+typedef struct nsm_cpacket {
+    uint32_t left0;
+    uint32_t right0;
+    uint32_t count;
+    uint32_t reserved_;
+    uint32_t rec[NSM_CPACKET_RECORDS];
+} nsm_cpacket_t; /* 256 bytes */
 
 /* One cohort side for intersection_vs_union: CSR items -> levels -> sorted unique token ids
  * (layout and meaning: napkon_string_matching/gpu/pack.py).  Levels are what
@@ -131,14 +151,22 @@ typedef struct nsm_job {
     double threshold;     /* keep score >= threshold (float64 compare, comparable_data.py:243) */
     const uint64_t *l_cat; /* [left.n_items] category bit masks */
     const uint64_t *r_cat; /* [right.n_items] */
-    void *out_pairs;       /* nsm_pair_t[out_capacity] or nsm_packet_t[out_capacity] (out_mode),
+    void *out_pairs;       /* nsm_pair_t / nsm_packet_t / nsm_cpacket_t [out_capacity] (out_mode),
                               16-byte aligned, filled densely in no particular order */
     uint64_t out_capacity;
-    uint64_t *out_count; /* number of kept pairs (NSM_OUT_PACKETS: of packets), also beyond capacity */
+    uint64_t *out_count; /* number of kept pairs (packet modes: of packets), also beyond capacity */
     uint32_t *out_flags; /* NSM_FLAG_* */
     uint64_t *out_stats; /* [NSM_N_STATS] counters; may be NULL with NSM_OUT_PAIRS */
     uint32_t out_mode;   /* NSM_OUT_* */
     uint32_t reserved_;
+    /* NSM_OUT_CODED only (ignored otherwise) */
+    uint64_t *out_dict;        /* [NSM_DICT_SLOTS] score dictionary.  NOT reset by the library: the
+                                  caller fills it with NSM_DICT_FREE before the first call of a
+                                  result and may share it between the row blocks of that result */
+    nsm_pair_t *out_exc;       /* [out_exc_capacity] pairs whose score found no dictionary slot */
+    uint64_t out_exc_capacity;
+    uint64_t *out_exc_count;   /* zeroed by the library; counts beyond the capacity too
+                                  (NSM_FLAG_OVERFLOW is then set) */
 } nsm_job_t;
 
 #define NSM_STAT_CANDIDATES 0   /* item pairs that reached exact float64 scoring */
@@ -163,6 +191,9 @@ int nsm_jaccard_allpairs(const nsm_sets_t *left, const nsm_sets_t *right, const 
  * normalised Indel similarity, bit-parallel LCS). */
 int nsm_qratio_allpairs(const nsm_strings_t *left, const nsm_strings_t *right, const nsm_job_t *job,
                         void *stream);
+
+/* Marks every slot of a score dictionary (NSM_OUT_CODED, uint64[NSM_DICT_SLOTS]) free. */
+int nsm_dict_reset(uint64_t *dict, void *stream);
 
 /* ---- device-side token packing ---------------------------------------------
  * Builds every array of nsm_sets_t on the GPU from the dictionary codes of the tokens, i.e. what

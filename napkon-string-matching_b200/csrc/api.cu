@@ -59,8 +59,14 @@ int prepare_job(const nsm_job_t *job, uint32_t n_left, cudaStream_t stream) {
         set_error("bad category mode or missing category masks");
         return NSM_ERR_BAD_ARG;
     }
-    if (job->out_mode > NSM_OUT_PACKETS) {
+    if (job->out_mode > NSM_OUT_CODED) {
         set_error("unknown out_mode %u", job->out_mode);
+        return NSM_ERR_BAD_ARG;
+    }
+    if (job->out_mode == NSM_OUT_CODED &&
+        (!job->out_dict || !job->out_exc_count || (job->out_exc_capacity && !job->out_exc) ||
+         (reinterpret_cast<uintptr_t>(job->out_exc) & 15u))) {
+        set_error("NSM_OUT_CODED needs out_dict, out_exc_count and a 16-byte aligned out_exc");
         return NSM_ERR_BAD_ARG;
     }
     if (reinterpret_cast<uintptr_t>(job->out_pairs) & 15u) {
@@ -71,6 +77,8 @@ int prepare_job(const nsm_job_t *job, uint32_t n_left, cudaStream_t stream) {
     NSM_CUDA_CHECK(cudaMemsetAsync(job->out_flags, 0, sizeof(uint32_t), stream));
     if (job->out_stats)
         NSM_CUDA_CHECK(cudaMemsetAsync(job->out_stats, 0, NSM_N_STATS * sizeof(uint64_t), stream));
+    if (job->out_mode == NSM_OUT_CODED)
+        NSM_CUDA_CHECK(cudaMemsetAsync(job->out_exc_count, 0, sizeof(uint64_t), stream));
     return NSM_OK;
 }
 
@@ -81,3 +89,10 @@ extern "C" int nsm_version(void) { return NSM_VERSION; }
 extern "C" const char *nsm_last_error(void) { return nsm::g_error; }
 
 extern "C" int nsm_last_launch_count(void) { return nsm::g_launches; }
+
+extern "C" int nsm_dict_reset(uint64_t *dict, void *stream) {
+    if (!dict) { nsm::set_error("null dictionary"); return NSM_ERR_BAD_ARG; }
+    NSM_CUDA_CHECK(cudaMemsetAsync(dict, 0xff, NSM_DICT_SLOTS * sizeof(uint64_t),
+                                   static_cast<cudaStream_t>(stream)));
+    return NSM_OK;
+}

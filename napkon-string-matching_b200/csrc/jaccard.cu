@@ -63,6 +63,7 @@ struct __align__(16) JaccardSmem {
     union {
         nsm_pair_t pairs[J_OUT];  // NSM_OUT_PAIRS: staged records of the warp
         nsm_packet_t packet;      // NSM_OUT_PACKETS: the packet the warp is filling
+        nsm_cpacket_t cpacket;    // NSM_OUT_CODED
     } out[J_WARPS];
     uint32_t r_info[J_SLOTS][JT_THREADS];  // size | fold count << 16
     uint32_t r_k[JT_THREADS];
@@ -245,7 +246,7 @@ jaccard_allpairs_kernel(const JaccardParams p) {
     uint32_t bar_parity = 0;
     unsigned long long st_cand = 0, st_evals = 0, st_merges = 0, st_bound = 0, st_kept = 0;
     uint32_t out_n = 0;  // warp-uniform fill of s.out[warp]
-    const bool packets = p.job.out_mode == NSM_OUT_PACKETS;
+    const bool packets = p.job.out_mode == NSM_OUT_PACKETS, coded = p.job.out_mode == NSM_OUT_CODED;
 
     auto flush_out = [&]() {
         if (out_n == 0) return;
@@ -284,6 +285,44 @@ jaccard_allpairs_kernel(const JaccardParams p) {
             atomicOr(p.job.out_flags, NSM_FLAG_OVERFLOW);
         }
         __syncwarp();
+    };
+
+    // NSM_OUT_CODED: 16 16-byte stores per packet
+    auto flush_cpacket = [&](uint32_t n_rec, uint32_t l0, uint32_t r0) {
+        nsm_cpacket_t &pk = s.out[warp].cpacket;
+        unsigned long long pos = 0;
+        if (lane == 0) {
+            pk.left0 = l0; pk.right0 = r0; pk.count = n_rec; pk.reserved_ = 0;
+            pos = atomicAdd(count, 1ull);
+        }
+        __syncwarp();
+        pos = __shfl_sync(FULL_MASK, pos, 0);
+        if (pos < p.job.out_capacity) {
+            constexpr uint32_t VECS = sizeof(nsm_cpacket_t) / 16;
+            static_assert(sizeof(nsm_cpacket_t) == 256, "16 vectors");
+            if (lane < VECS)
+                reinterpret_cast<uint4 *>(reinterpret_cast<nsm_cpacket_t *>(p.job.out_pairs) + pos)[lane] =
+                    reinterpret_cast<const uint4 *>(&pk)[lane];
+        } else if (lane == 0) {
+            atomicOr(p.job.out_flags, NSM_FLAG_OVERFLOW);
+        }
+        __syncwarp();
+    };
+    // Slot of a score in the dictionary (its 16-bit code), inserting it when a slot within reach
+    // of its hash is free; 0xffffffff when there is none (the pair then goes out uncoded).
+    // Keys are only ever added, so a slot that shows the key — even from a stale cache line — is right.
+    auto dict_code = [&](double score) -> uint32_t {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(score);
+        unsigned long long *table = reinterpret_cast<unsigned long long *>(p.job.out_dict);
+        const uint32_t h = (uint32_t)((bits * 0x9E3779B97F4A7C15ull) >> 48);
+#pragma unroll 1
+        for (uint32_t probe = 0; probe < 8; ++probe) {
+            const uint32_t slot = (h + probe) & (NSM_DICT_SLOTS - 1u);
+            unsigned long long k = __ldcg(table + slot);
+            if (k == NSM_DICT_FREE) k = atomicCAS(table + slot, NSM_DICT_FREE, bits), k = k == NSM_DICT_FREE ? bits : k;
+            if (k == bits) return slot;
+        }
+        return 0xffffffffu;
     };
 
     // summary of one item at step t >= 1: from the slot arrays, or from the CSR arrays when the
@@ -686,7 +725,26 @@ jaccard_allpairs_kernel(const JaccardParams p) {
                 if (m) {
                     const uint32_t n = __popc(m), slot = out_n + __popc(m & lanemask_lt());
                     st_kept += keep ? 1u : 0u;
-                    if (packets) {
+                    if (coded) {
+                        // unit-local 16-bit position + 16-bit score code; uncoded pairs as nsm_pair_t
+                        const uint32_t code = keep ? dict_code(score) : 0u;
+                        const bool exc = keep && code == 0xffffffffu, in = keep && !exc;
+                        emit_pairs(exc, c_l, c_r, score, p.job.out_exc, p.job.out_exc_capacity,
+                                   reinterpret_cast<unsigned long long *>(p.job.out_exc_count), p.job.out_flags);
+                        const unsigned mi = __ballot_sync(FULL_MASK, in);
+                        const uint32_t ni = __popc(mi), sl = out_n + __popc(mi & lanemask_lt());
+                        nsm_cpacket_t &pk = s.out[warp].cpacket;
+                        const uint32_t rec = (code << 16) | (li << 7) | rc;
+                        if (in && sl < (uint32_t)NSM_CPACKET_RECORDS) pk.rec[sl] = rec;
+                        if (out_n + ni >= (uint32_t)NSM_CPACKET_RECORDS) {
+                            __syncwarp();
+                            flush_cpacket(NSM_CPACKET_RECORDS, l0, r0);
+                            if (in && sl >= (uint32_t)NSM_CPACKET_RECORDS) pk.rec[sl - NSM_CPACKET_RECORDS] = rec;
+                            out_n = out_n + ni - NSM_CPACKET_RECORDS;
+                        } else {
+                            out_n += ni;
+                        }
+                    } else if (packets) {
                         // unit-local 16-bit position + score; the packet is filled to its last slot
                         nsm_packet_t &pk = s.out[warp].packet;
                         const uint16_t loc = (uint16_t)((li << 7) | rc);
@@ -716,13 +774,13 @@ jaccard_allpairs_kernel(const JaccardParams p) {
                 __syncwarp();
             }
         }
-        if (packets && out_n) {  // positions are unit-local: the warp's partial packet ends here
+        if ((packets || coded) && out_n) {  // positions are unit-local: the warp's partial packet ends here
             __syncwarp();
-            flush_packet(out_n, l0, r0);
+            if (coded) flush_cpacket(out_n, l0, r0); else flush_packet(out_n, l0, r0);
             out_n = 0;
         }
     }
-    if (!packets) flush_out();
+    if (!packets && !coded) flush_out();
 
     if (p.job.out_stats) {
         atomicAdd(&s.stats[NSM_STAT_CANDIDATES], st_cand);
@@ -767,8 +825,8 @@ extern "C" int nsm_jaccard_allpairs(const nsm_sets_t *left, const nsm_sets_t *ri
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (!left || !right || !job) { set_error("null argument"); return NSM_ERR_BAD_ARG; }
     if (int rc = prepare_job(job, left->n_items, stream)) return rc;
-    if (job->out_mode == NSM_OUT_PACKETS && !job->out_stats) {
-        set_error("NSM_OUT_PACKETS needs out_stats (the kept-pair count is NSM_STAT_KEPT)");
+    if (job->out_mode != NSM_OUT_PAIRS && !job->out_stats) {
+        set_error("the packet modes need out_stats (the kept-pair count is NSM_STAT_KEPT)");
         return NSM_ERR_BAD_ARG;
     }
     if (job->l_row_begin == job->l_row_end || right->n_items == 0) return NSM_OK;

@@ -59,22 +59,25 @@ class Records:
     (valid until its next call), part by part in the wire format of the part — ``PAIR_DTYPE``
     records or ``nsm_packet_t`` packets (include/nsm.h)."""
 
-    def __init__(self, parts, count: int, left_perm=None, right_perm=None):
+    def __init__(self, parts, count: int, left_perm=None, right_perm=None, dictionary=None):
         self.parts, self.count = parts, int(count)
         self.left_perm, self.right_perm = left_perm, right_perm
+        self.dictionary = dictionary   # uint64[DICT_SLOTS]: the scores behind NSM_OUT_CODED parts
 
     def __len__(self) -> int:
         return self.count
 
     @property
     def nbytes(self) -> int:
-        return sum(a.nbytes for _, a in self.parts)
+        return sum(a.nbytes for _, a in self.parts) + (self.dictionary.nbytes if self.dictionary is not None else 0)
 
     def decode(self, copy: bool = True) -> np.ndarray:
         """All parts as one ``PAIR_DTYPE`` array with the callers' item indices."""
         if not self.parts:
             return np.zeros(0, dtype=PAIR_DTYPE)
-        arrays = [nsmlib.decode_packets(a) if mode == nsmlib.OUT_PACKETS else a for mode, a in self.parts]
+        arrays = [nsmlib.decode_packets(a) if mode == nsmlib.OUT_PACKETS else
+                  nsmlib.decode_cpackets(a, self.dictionary) if mode == nsmlib.OUT_CODED else a
+                  for mode, a in self.parts]
         if len(arrays) == 1:
             plain = self.parts[0][0] == nsmlib.OUT_PAIRS
             out = arrays[0].copy() if (plain and (copy or self.left_perm is not None)) else arrays[0]
@@ -97,8 +100,10 @@ class Engine:
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         self.max_pairs_per_block = int(max_pairs_per_block)
         self.pipeline_d2h = True    # probe + row blocks for results that go to the host
-        # record format of dense results that go to the host: "auto" (packets when the probe block
-        # finds >= 2 packets per warp and unit), True (packets for every token-set job), False
+        # record format of token-set results that go to the host (include/nsm.h NSM_OUT_*):
+        # "auto": coded packets (4.3 B per kept pair) when the probe block finds the result dense
+        # (>= 2 packets per warp and unit), else 16-byte pairs; "coded" / True or "packets": that
+        # format for every token-set job; False: always 16-byte pairs
         self.compact = "auto"
         self._buffers: Dict[str, torch.Tensor] = {}
         self.launches = 0           # kernels of ours launched so far
@@ -230,7 +235,10 @@ class Engine:
         ctl = [self._arena(f"ctl{i}", 64, pinned=False) for i in range(2)]
         ctl_pin = [self._arena(f"ctl_pin{i}", 64, pinned=True) for i in range(2)]
         slot_free: List[Optional[torch.cuda.Event]] = [None, None]   # D2H out of the arena done
-        rec_bytes = (16, nsmlib.PACKET_DTYPE.itemsize)
+        rec_bytes, entry_records = nsmlib.RECORD_BYTES, nsmlib.ENTRY_RECORDS
+        dicts: Dict[int, torch.Tensor] = {}      # job -> device score dictionary (NSM_OUT_CODED)
+        dict_host: Dict[int, int] = {}           # job -> offset of its copy in the pinned arena
+        dict_bytes = nsmlib.DICT_SLOTS * 8
 
         def n_units(rows: int, n_right: int) -> int:
             return -(-rows // nsmlib.UNIT_LEFT) * -(-n_right // nsmlib.UNIT_RIGHT)
@@ -238,8 +246,8 @@ class Engine:
         def capacity_for(mode: int, records: float, rows: int, n_right: int) -> int:
             """Arena entries (pairs or packets) that hold `records` kept pairs of a row block."""
             records = min(float(self.max_pairs_per_block), records)
-            if mode == nsmlib.OUT_PACKETS:   # full packets + at most one partial per warp and unit
-                return int(records / nsmlib.PACKET_RECORDS) + 4 * n_units(rows, n_right) + 64
+            if mode != nsmlib.OUT_PAIRS:   # full packets + at most one partial per warp and unit
+                return int(records / entry_records[mode]) + 4 * n_units(rows, n_right) + 64
             return max(int(records) + 4096, 1 << 18)
 
         # Work items: row blocks of the jobs.  A job whose records go to the host starts with a
@@ -254,12 +262,14 @@ class Engine:
                 raise TypeError("left and right must be packed for the same score function")
             begin, end = job.rows if job.rows is not None else (0, job.left.n_items)
             infos.append({"count": 0, "flags": 0, "reruns": 0, "blocks": 0, "d2h_bytes": 0,
-                          "packets": 0, "stats": dict.fromkeys(nsmlib.STAT_NAMES, 0),
+                          "packets": 0, "uncoded": 0, "stats": dict.fromkeys(nsmlib.STAT_NAMES, 0),
                           "item_pairs": max(0, end - begin) * job.right.n_items, "parts": []})
             if end <= begin or not job.right.n_items:
                 continue
             rows = end - begin
-            forced = nsmlib.OUT_PACKETS if (self.compact is True and job.left.kind == "sets") else nsmlib.OUT_PAIRS
+            forced = nsmlib.OUT_PAIRS
+            if job.left.kind == "sets" and self.compact in (True, "coded", "packets"):
+                forced = nsmlib.OUT_PACKETS if self.compact == "packets" else nsmlib.OUT_CODED
             if (to_host and self.pipeline_d2h and capacity is None and rows >= 4 * nsmlib.UNIT_LEFT
                     and rows * job.right.n_items >= self.PIPELINE_MIN_PAIRS):
                 cut = begin + max(nsmlib.UNIT_LEFT, rows // 16 // nsmlib.UNIT_LEFT * nsmlib.UNIT_LEFT)
@@ -278,11 +288,20 @@ class Engine:
             dev = self._arena(f"out{slot}", item["cap"] * rec_bytes[mode], pinned=False)
             cap = dev.numel() // rec_bytes[mode]
             c = ctl[slot]
+            coded = (None, None, 0, None)
+            if mode == nsmlib.OUT_CODED:
+                if item["j"] not in dicts:   # one dictionary per result, shared by its row blocks
+                    dicts[item["j"]] = torch.empty(dict_bytes, dtype=torch.uint8, device=self.device)
+                    nsmlib.check(self.lib.nsm_dict_reset(dicts[item["j"]].data_ptr(),
+                                                         C.c_void_p(stream.cuda_stream)))
+                item.setdefault("exc_cap", max(1 << 16, cap * entry_records[mode] // 16))
+                exc = self._arena(f"exc{slot}", item["exc_cap"] * 16, pinned=False)
+                coded = (dicts[item["j"]].data_ptr(), exc.data_ptr(), exc.numel() // 16, c.data_ptr() + 56)
             cjob = nsmlib.NsmJob(item["rb"], item["re"], int(job.flat), int(job.cat_mode), float(job.threshold),
                                  job.l_cat.data_ptr() if job.l_cat is not None else None,
                                  job.r_cat.data_ptr() if job.r_cat is not None else None,
                                  dev.data_ptr(), cap, c.data_ptr(), c.data_ptr() + 8, c.data_ptr() + 16,
-                                 mode, 0)
+                                 mode, 0, *coded)
             if self.time_kernels:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream)
@@ -337,6 +356,7 @@ class Engine:
             stats = [int(x) for x in words[2:2 + nsmlib.N_STATS]]
             j, rb, re_, mode = p_item["j"], p_item["rb"], p_item["re"], p_item["mode"]
             job, info = jobs[j], infos[j]
+            n_exc = int(words[7]) if mode == nsmlib.OUT_CODED else 0
             i_kept = nsmlib.STAT_NAMES.index("kept")
             if mode == nsmlib.OUT_PAIRS:
                 stats[i_kept] = count    # the fuzzy kernel does not keep this counter
@@ -349,10 +369,12 @@ class Engine:
                 if count > limit and re_ - rb > 1:
                     n_parts = min(re_ - rb, -(-count // max(1, limit // 2)))
                     cuts = np.linspace(rb, re_, n_parts + 1).astype(np.int64)
-                    queue[:0] = [{"j": j, "rb": int(a), "re": int(b), "mode": mode, "cap": limit}
+                    queue[:0] = [{"j": j, "rb": int(a), "re": int(b), "mode": mode, "cap": limit,
+                                  "exc_cap": int(n_exc * 1.1) + 1024}
                                  for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
                 else:
-                    queue.insert(0, {**p_item, "cap": int(count * 1.02) + 1024})
+                    queue.insert(0, {**p_item, "cap": int(count * 1.02) + 1024,
+                                     "exc_cap": int(n_exc * 1.1) + 1024})
                 pending = None
                 slot = p_slot
                 continue
@@ -363,9 +385,9 @@ class Engine:
                 expect = density * rest_rows * job.right.n_items        # kept pairs still to come
                 r_mode = rest["mode"]
                 if (self.compact == "auto" and job.left.kind == "sets" and
-                        density * nsmlib.UNIT_LEFT * 32 >= 2 * nsmlib.PACKET_RECORDS):
-                    r_mode = nsmlib.OUT_PACKETS   # >= two packets per warp and unit: < 14 B per pair
-                per_rec = 16 if r_mode == nsmlib.OUT_PAIRS else rec_bytes[1] / nsmlib.PACKET_RECORDS
+                        density * nsmlib.UNIT_LEFT * 32 >= 2 * nsmlib.CPACKET_RECORDS):
+                    r_mode = nsmlib.OUT_CODED   # >= two packets per warp and unit
+                per_rec = rec_bytes[r_mode] / entry_records[r_mode]
                 n_parts = int(min(16, max(1, -(-(expect * per_rec) // self.PIPELINE_BLOCK_BYTES))))
                 step = -(-rest_rows // n_parts)
                 step = -(-step // nsmlib.UNIT_LEFT) * nsmlib.UNIT_LEFT   # whole 512-row chunks
@@ -377,6 +399,8 @@ class Engine:
                              for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
                 if to_host:   # one allocation of page-locked memory for everything still to come
                     ahead = sum(q["cap"] * rec_bytes[q["mode"]] for q in queue if q["j"] == j and "cap" in q)
+                    if r_mode == nsmlib.OUT_CODED:   # uncoded pairs (a few per cent) + the dictionary
+                        ahead += int(expect * margin * 0.1) * 16 + dict_bytes
                     reserve_host(count * 16 + ahead, host_fill)
             # launch the next block before copying this one out, so that the two overlap
             if queue:
@@ -389,21 +413,35 @@ class Engine:
             info["blocks"] += 1
             for name, v in zip(nsmlib.STAT_NAMES, stats):
                 info["stats"][name] += v
-            if mode == nsmlib.OUT_PACKETS:
+            if mode != nsmlib.OUT_PAIRS:
                 info["packets"] += count
-            if to_host and count:
-                n_bytes = count * rec_bytes[mode]
-                pin = reserve_host(n_bytes, host_fill)
+                info["uncoded"] += n_exc
+            if to_host and (count or n_exc):
+                n_bytes, x_bytes = count * rec_bytes[mode], n_exc * 16
+                extra = dict_bytes if (mode == nsmlib.OUT_CODED and j not in dict_host) else 0
+                pin = reserve_host(n_bytes + x_bytes + extra, host_fill)
+                if extra:
+                    dict_host[j] = host_fill
+                    host_fill += dict_bytes
+                    info["d2h_bytes"] += dict_bytes
                 copy_stream.wait_event(p_done)
                 with torch.cuda.stream(copy_stream):
                     pin[host_fill:host_fill + n_bytes].copy_(self._buffers[f"out{p_slot}"][:n_bytes],
                                                              non_blocking=True)
+                    if x_bytes:
+                        pin[host_fill + n_bytes:host_fill + n_bytes + x_bytes].copy_(
+                            self._buffers[f"exc{p_slot}"][:x_bytes], non_blocking=True)
+                    if mode == nsmlib.OUT_CODED:   # the dictionary as of this block (it only grows)
+                        pin[dict_host[j]:dict_host[j] + dict_bytes].copy_(dicts[j], non_blocking=True)
                     freed = torch.cuda.Event()
                     freed.record(copy_stream)
                 slot_free[p_slot] = freed
-                info["parts"].append((host_fill, n_bytes, mode))
-                info["d2h_bytes"] += n_bytes
-                host_fill += n_bytes
+                if n_bytes:
+                    info["parts"].append((host_fill, n_bytes, mode))
+                if x_bytes:
+                    info["parts"].append((host_fill + n_bytes, x_bytes, nsmlib.OUT_PAIRS))
+                info["d2h_bytes"] += n_bytes + x_bytes
+                host_fill += n_bytes + x_bytes
             pending = nxt
         copy_stream.synchronize()
         for ev in slot_free:
@@ -416,13 +454,14 @@ class Engine:
             self._timed.clear()
 
         outs = []
-        for job, info in zip(jobs, infos):
+        wire = (PAIR_DTYPE, nsmlib.PACKET_DTYPE, nsmlib.CPACKET_DTYPE)
+        for j, (job, info) in enumerate(zip(jobs, infos)):
             parts = info.pop("parts")
             pin = self._buffers.get("pin")
-            views = [(mode, pin[lo:lo + n].numpy().view(PAIR_DTYPE if mode == nsmlib.OUT_PAIRS
-                                                        else nsmlib.PACKET_DTYPE))
-                     for lo, n, mode in parts] if to_host else []
-            rec = Records(views, info["count"] if to_host else 0, job.left.perm, job.right.perm)
+            views = [(mode, pin[lo:lo + n].numpy().view(wire[mode])) for lo, n, mode in parts] if to_host else []
+            dictionary = pin[dict_host[j]:dict_host[j] + dict_bytes].numpy().view(np.uint64) \
+                if (to_host and j in dict_host) else None
+            rec = Records(views, info["count"] if to_host else 0, job.left.perm, job.right.perm, dictionary)
             outs.append(rec.decode(copy=copy) if decode else rec)
         return outs
 

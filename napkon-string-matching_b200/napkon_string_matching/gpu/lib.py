@@ -22,8 +22,16 @@ PAIR_DTYPE = np.dtype([("left", np.uint32), ("right", np.uint32), ("score", np.f
 assert PAIR_DTYPE.itemsize == 16
 
 # NSM_OUT_PACKETS (include/nsm.h:nsm_packet_t): up to 48 kept pairs of one 512 x 128 block
-OUT_PAIRS, OUT_PACKETS = 0, 1
+OUT_PAIRS, OUT_PACKETS, OUT_CODED = 0, 1, 2
 PACKET_RECORDS = 48
+CPACKET_RECORDS = 60
+DICT_SLOTS = 65536
+# NSM_OUT_CODED (nsm_cpacket_t): 16-bit position + 16-bit score code per kept pair
+CPACKET_DTYPE = np.dtype([("left0", np.uint32), ("right0", np.uint32), ("count", np.uint32),
+                          ("reserved_", np.uint32), ("rec", np.uint32, (CPACKET_RECORDS,))])
+assert CPACKET_DTYPE.itemsize == 256
+RECORD_BYTES = (16, 496, 256)                           # arena entry per out_mode
+ENTRY_RECORDS = (1, PACKET_RECORDS, CPACKET_RECORDS)    # kept pairs one entry can hold
 PACKET_DTYPE = np.dtype([("left0", np.uint32), ("right0", np.uint32), ("count", np.uint32),
                          ("reserved_", np.uint32), ("score", np.float64, (PACKET_RECORDS,)),
                          ("local", np.uint16, (PACKET_RECORDS,))])
@@ -42,13 +50,25 @@ def decode_packets(packets: np.ndarray) -> np.ndarray:
     out["score"] = packets["score"][used]
     return out
 
+
+def decode_cpackets(packets: np.ndarray, dictionary: np.ndarray) -> np.ndarray:
+    """``nsm_cpacket_t`` records + the score dictionary (uint64[DICT_SLOTS]) -> ``PAIR_DTYPE``."""
+    count = packets["count"].astype(np.int64)
+    used = np.arange(CPACKET_RECORDS, dtype=np.int64)[None, :] < count[:, None]
+    rec = packets["rec"][used]
+    out = np.empty(len(rec), dtype=PAIR_DTYPE)
+    out["left"] = np.repeat(packets["left0"], count) + ((rec & np.uint32(0xffff)) >> np.uint32(7))
+    out["right"] = np.repeat(packets["right0"], count) + (rec & np.uint32(127))
+    out["score"] = np.ascontiguousarray(dictionary).view(np.float64)[rec >> np.uint32(16)]
+    return out
+
 RAW_SUFFIX_PARTS, RAW_LEVELS = 0, 1
 PACK_MAX_ITEM_IDS = 1024
 PACK_FLAG_TOO_LARGE, PACK_FLAG_NOT_NESTED, PACK_FLAG_BAD_ID = 1, 2, 4
 
 EXPORTS = ("nsm_version", "nsm_last_error", "nsm_last_launch_count", "nsm_jaccard_allpairs",
            "nsm_qratio_allpairs", "nsm_microbench", "nsm_pack_count_ids", "nsm_pack_scratch_bytes",
-           "nsm_pack_sets_measure", "nsm_pack_sets_fill")
+           "nsm_pack_sets_measure", "nsm_pack_sets_fill", "nsm_dict_reset")
 
 
 class NsmSets(C.Structure):
@@ -80,7 +100,9 @@ class NsmJob(C.Structure):
                 ("cat_mode", C.c_uint32), ("threshold", C.c_double), ("l_cat", C.c_void_p),
                 ("r_cat", C.c_void_p), ("out_pairs", C.c_void_p), ("out_capacity", C.c_uint64),
                 ("out_count", C.c_void_p), ("out_flags", C.c_void_p), ("out_stats", C.c_void_p),
-                ("out_mode", C.c_uint32), ("reserved_", C.c_uint32)]
+                ("out_mode", C.c_uint32), ("reserved_", C.c_uint32),
+                ("out_dict", C.c_void_p), ("out_exc", C.c_void_p), ("out_exc_capacity", C.c_uint64),
+                ("out_exc_count", C.c_void_p)]
 
 
 class NsmError(RuntimeError):
@@ -107,6 +129,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(first), C.POINTER(first), C.POINTER(NsmJob), C.c_void_p]
+    lib.nsm_dict_reset.restype = C.c_int
+    lib.nsm_dict_reset.argtypes = [C.c_void_p, C.c_void_p]
     lib.nsm_microbench.restype = C.c_int
     lib.nsm_microbench.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
                                    C.POINTER(C.c_uint64), C.c_void_p]

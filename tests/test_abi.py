@@ -36,7 +36,8 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(nsmlib.NsmStrings) == 4 * 8 + 6 * 4 + 8 * 4
     assert nsmlib.NsmJob.threshold.offset == 16
     assert nsmlib.NsmJob.out_pairs.offset == 40
-    assert ctypes.sizeof(nsmlib.NsmJob) == 88
+    assert ctypes.sizeof(nsmlib.NsmJob) == 120 and nsmlib.NsmJob.out_dict.offset == 88
+    assert nsmlib.CPACKET_DTYPE.itemsize == 256
     assert nsmlib.NsmJob.out_mode.offset == 80
     assert nsmlib.PACKET_DTYPE.itemsize == 496 and nsmlib.PACKET_DTYPE.fields["local"][1] == 400
     assert ctypes.sizeof(nsmlib.NsmRawSets) == 4 * 8 + 6 * 4

@@ -37,6 +37,27 @@ def test_decode_packets_on_hand_built_packets():
     assert len(nsmlib.decode_packets(pk[:0])) == 0
 
 
+def test_decode_cpackets_on_hand_built_packets():
+    rng = np.random.default_rng(6)
+    table = np.full(nsmlib.DICT_SLOTS, 0xffffffffffffffff, dtype=np.uint64)
+    slots = rng.choice(nsmlib.DICT_SLOTS, size=500, replace=False)
+    table[slots] = rng.random(500).view(np.uint64)
+    n = 29
+    pk = np.zeros(n, dtype=nsmlib.CPACKET_DTYPE)
+    want = []
+    for i in range(n):
+        cnt = int(rng.integers(0, nsmlib.CPACKET_RECORDS + 1)) if i % 4 else nsmlib.CPACKET_RECORDS
+        l0, r0 = int(rng.integers(0, 1 << 20)) * 512, int(rng.integers(0, 1 << 18)) * 128
+        pk[i]["left0"], pk[i]["right0"], pk[i]["count"] = l0, r0, cnt
+        pk[i]["rec"][:] = 0xffffffff
+        for s_ in range(cnt):
+            li, rc, code = int(rng.integers(0, 512)), int(rng.integers(0, 128)), int(rng.choice(slots))
+            pk[i]["rec"][s_] = (code << 16) | (li << 7) | rc
+            want.append((l0 + li, r0 + rc, float(table[code:code + 1].view(np.float64)[0])))
+    out = nsmlib.decode_cpackets(pk, table)
+    assert [(int(a), int(b), float(c)) for a, b, c in zip(out["left"], out["right"], out["score"])] == want
+
+
 def _tokenid_packs(nl, nr):
     lens, flat = syn.token_id_level_sets(nl, syn.SEED_LEFT)
     pl = pack.pack_suffix_id_sets(lens, flat, 30000)
@@ -56,19 +77,26 @@ def test_packets_equal_pairs_and_oracle(engine):
         engine.compact = False
         plain = engine.all_pairs(dl, dr, 0.1)
         assert engine.last_info["packets"] == 0
-        engine.compact = True
+        engine.compact = "packets"
         packed = engine.all_pairs(dl, dr, 0.1)
         info = engine.last_info
         assert info["packets"] > 0 and info["count"] == len(packed)
         # full packets except at most one per warp and unit
         assert info["packets"] <= len(packed) // nsmlib.PACKET_RECORDS + 4 * 3 * 9
+        engine.compact = "coded"
+        coded = engine.all_pairs(dl, dr, 0.1)
+        info = engine.last_info
+        assert info["packets"] > 0 and info["count"] == len(coded)
+        assert info["packets"] <= (len(coded) - info["uncoded"]) // nsmlib.CPACKET_RECORDS + 4 * 3 * 9
+        assert info["uncoded"] < 0.05 * len(coded)
+        assert info["d2h_bytes"] < 5.5 * len(coded) + nsmlib.DICT_SLOTS * 8
         # a row block and an overflowing arena (exact re-run) in packet mode
         engine._buffers.pop("out0", None), engine._buffers.pop("out1", None)   # arenas only grow
         block = engine.all_pairs(dl, dr, 0.1, rows=(300, 1301), capacity=64)
         assert engine.last_info["reruns"] == 1
     finally:
         engine.compact = old
-    for got in (plain, packed):
+    for got in (plain, packed, coded):
         assert_same_triples((got["left"], got["right"], got["score"]),
                             (want["left"], want["right"], want["score"]))
     sel = (want["left"] >= 300) & (want["left"] < 1301)
@@ -97,7 +125,7 @@ def test_probe_sized_pipeline_has_no_reruns(engine, monkeypatch):
     finally:
         engine.compact = old
     assert info["reruns"] == 0 and info["blocks"] >= 3 and info["packets"] > 0
-    assert info["d2h_bytes"] < 13 * len(plain)          # < 13 bytes per kept pair on the wire
+    assert info["d2h_bytes"] < 6 * len(plain) + nsmlib.DICT_SLOTS * 8   # ~4.5 bytes per kept pair on the wire
     assert_same_triples((piped["left"], piped["right"], piped["score"]),
                         (plain["left"], plain["right"], plain["score"]))
     # sparse results stay in the 16-byte format
@@ -131,7 +159,7 @@ NCCL_WORKER = textwrap.dedent("""
         packs.append(pack.pack_suffix_id_sets(lens, flat, 30000))
     dev = [eng.upload(p) for p in packs]
     pairs = [(0, 1), (0, 2), (1, 2)]
-    eng.compact = True if os.environ.get("NSM_TEST_COMPACT") == "1" else "auto"
+    eng.compact = os.environ.get("NSM_TEST_COMPACT") or "auto"
     outs, counts = distributed.sharded_run_jobs(eng, [Job(dev[a], dev[b], 0.1) for a, b in pairs])
     assert len(counts) == dist.get_world_size()
     key = lambda a: np.lexsort((a["right"], a["left"]))
@@ -158,7 +186,7 @@ NCCL_WORKER = textwrap.dedent("""
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("compact", ["0", "1"])
+@pytest.mark.parametrize("compact", ["auto", "coded", "packets"])
 def test_sharded_run_jobs_on_real_gpus(tmp_path, compact):
     import torch
 
