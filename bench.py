@@ -587,6 +587,8 @@ class Prepared:
             d = dict(zip(self.names, self.eng.device_packer.pack(self.raw_sets, self.n_vocab, rank=self.rank_mode)))
         else:
             d = {k: self.eng.upload(p, self.pinned[k]) for k, p in self.packs.items()}
+        if self.eng.trace is not None:
+            self.eng._mark("inputs uploaded / packed (launched)")
         outs, counts = distributed.sharded_run_jobs(self.eng, self.jobs(d), to_host=True, decode=False)
         self.last_records = outs
         infos = self.eng.last_infos
@@ -678,6 +680,14 @@ def measure(prep: Prepared, steps: int, warmup: int, rank: int, world: int, int_
     ms_e2e, (counts_e2e, d2h, packets, reruns, uncoded) = timed(prep.step_e2e, not self_flushing)
     barrier()
     t1 = time.time()
+    # host-side timeline of one more (untimed) end-to-end step: where the step's wall time goes
+    eng.trace = []
+    t_step = time.perf_counter()
+    prep.step_e2e()
+    torch.cuda.synchronize()
+    timeline = [(round((t - t_step) * 1e3, 2), label) for t, label in eng.trace]
+    timeline.append((round((time.perf_counter() - t_step) * 1e3, 2), "step returned"))
+    eng.trace = None
     eng.time_kernels = False
     e2e_kernel_ms, e2e_kernel_launches, e2e_launches = eng.kernel_ms, eng.kernel_launches_timed, eng.launches - launches0
     if not separate_resident:
@@ -738,7 +748,8 @@ def measure(prep: Prepared, steps: int, warmup: int, rank: int, world: int, int_
                                   % (d2h_sum / max(1, kept), packets_sum, uncoded_sum)) if packets_sum else
                                  "nsm_pair_t: 16 bytes per kept pair",
                 "kernel_ms_per_step": e2e_kernel_ms / steps, "overflow_reruns_per_step": reruns_sum / steps,
-                "collective": "NCCL all-gather of the kept-pair counts, every step" if world > 1 else None},
+                "collective": "NCCL all-gather of the kept-pair counts, every step" if world > 1 else None,
+                "timeline_ms_rank0": timeline},
         "pack": prep.pack_info,
         "gpu_launches": int(launches_sum),
         "clocks": clocks,

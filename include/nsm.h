@@ -129,15 +129,20 @@ typedef struct nsm_strings {
     const uint32_t *level_chr_off;  /* [n_levels] start of the level's string in chr, multiple of 8 */
     const uint32_t *level_len;      /* [n_levels] length in code points */
     const uint8_t *chr;             /* codes < n_alphabet; every string padded to 8 bytes */
+    const uint32_t *level_hist;     /* [n_levels][8]: 32 byte counters (saturating at 255) of the level
+                                       string's codes, bucket = code & 31 (byte b of word q = bucket
+                                       4 q + b): the sound distance bound of the flat kernel */
     uint32_t n_items;
     uint32_t n_levels;
     uint32_t max_levels;
     uint32_t max_len;    /* longest level string on this side */
-    uint32_t n_alphabet; /* shared by both sides, <= 255 */
+    uint32_t n_alphabet; /* codes in use, shared by both sides, <= 255 (code points that occur on one
+                            side only share one code per side: they can never match) */
     uint32_t reserved_;
-    /* Items are ordered by the 64-bit words their longest level string needs: items
-     * [class_end[w-1], class_end[w]) need w+1 words (class_end[7] == n_items; longer strings are
-     * not supported).  The kernel runs every class of the right side with its own width. */
+    /* Items are ordered by the length of their longest level string, so also by the 64-bit words it
+     * needs: items [class_end[w-1], class_end[w]) need w+1 words; items from class_end[7] on hold a
+     * level string of more than 512 characters.  The kernels run every class of the right side with
+     * its own width; pairs with a long item go through the swapped / warp-cooperative passes. */
     uint32_t class_end[8];
 } nsm_strings_t;
 

@@ -17,273 +17,17 @@
 // Strings longer than 64 characters use W words per thread with the add carry chained through
 // registers (W is a template parameter, <= 8, i.e. 512 characters).
 //
-// Two instantiations per W:
-//   LEVELS = false  items have one level (the flat score function, the `Question` column of
-//                   config 3): masks are built once per unit, every pair is scored and emitted
-//                   as soon as its LCS is known.
+// Items with one level each (the flat score function, config 3's `Question` strings) go through
+// qratio_flat.cu, which prunes with a sound distance bound; pairs whose items both hold a level
+// string of more than 512 characters through qratio_long.cu (one warp per pair).  This file:
 //   LEVELS = true   compare_terms' schedule runs as the outer loop per left tile (step t uses
 //                   level min(t, K-1) on both sides, weight 2^-t); a thread rebuilds its masks at
 //                   most K_right times per tile; partial scores of the tile's pairs live in
 //                   shared memory as float64 and are accumulated in the reference's order.
 // Pairs with score >= threshold are compacted with one atomic per warp.
-#include "nsm_common.cuh"
+#include "qratio_common.cuh"
 
 namespace nsm {
-
-constexpr int Q_MAX_THREADS = 512;
-constexpr int Q_TILE_FLAT = 32;       // left items per tile, one level each
-constexpr int Q_TILE_LEVELS = 8;      // left items per tile when partial scores are kept
-constexpr int Q_GROUP = 16;           // left tiles per unit
-constexpr int Q_CHR_CAP = 16 * 1024;  // bytes of left level strings staged per tile
-constexpr int Q_LEV_CAP = 1024;       // left levels staged per tile
-constexpr int Q_MAX_WORDS = 8;
-constexpr size_t Q_SMEM_BUDGET = 220 * 1024;
-
-struct QratioParams {
-    nsm_strings_t L, R;
-    nsm_job_t job;
-    uint32_t tile_left, n_ltiles, n_lgroups, n_rblocks;
-    uint32_t threads;   // right items per block
-    uint32_t n_alpha;   // rows of the mask table
-    uint32_t r_begin, r_end;  // the right items of this launch (one word-count class)
-};
-
-struct QratioLayout {  // offsets into dynamic shared memory
-    size_t pm, acc, chr, lev_off, lev_len, item_g0, cat, misc, total;
-};
-
-__host__ __device__ inline QratioLayout qratio_layout(uint32_t n_alpha, uint32_t words,
-                                                      uint32_t threads, uint32_t tile_left,
-                                                      bool levels) {
-    QratioLayout l;
-    size_t o = 0;
-    l.pm = o;      o += (size_t)n_alpha * words * threads * 8;
-    l.acc = o;     o += levels ? (size_t)tile_left * threads * 8 : 0;
-    l.chr = o;     o += Q_CHR_CAP;
-    l.cat = o;     o += Q_TILE_FLAT * 8;
-    l.lev_off = o; o += Q_LEV_CAP * 4;
-    l.lev_len = o; o += Q_LEV_CAP * 4;
-    l.item_g0 = o; o += (Q_TILE_FLAT + 1) * 4;
-    l.misc = o;    o += 16;
-    l.total = (o + 15) & ~(size_t)15;
-    return l;
-}
-
-// sum = S + u over W 64-bit words as ONE multi-word addition: the carry runs through the
-// hardware carry flag (add.cc / addc.cc on the 32-bit halves), two instructions per word instead
-// of an add plus compares and selects per word.  HALVES = 2 * words of one block (<= 8).
-__device__ __forceinline__ uint32_t lo32(uint64_t v) { return (uint32_t)v; }
-__device__ __forceinline__ uint32_t hi32(uint64_t v) { return (uint32_t)(v >> 32); }
-__device__ __forceinline__ uint64_t mk64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
-
-// one block of two words; carry_in / carry_out are 0 or 1
-__device__ __forceinline__ void add2(const uint64_t *a, const uint64_t *b, uint64_t *r, uint32_t cin,
-                                     uint32_t &cout) {
-    uint32_t r0, r1, r2, r3, t;  // t: scratch of the flag-setting add
-    asm("{\n\t"
-        "add.cc.u32 %5, %14, 0xffffffff;\n\t"   // carry flag = carry_in
-        "addc.cc.u32 %0, %6, %10;\n\t"
-        "addc.cc.u32 %1, %7, %11;\n\t"
-        "addc.cc.u32 %2, %8, %12;\n\t"
-        "addc.cc.u32 %3, %9, %13;\n\t"
-        "addc.u32 %4, 0, 0;\n\t"
-        "}"
-        : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(cout), "=r"(t)
-        : "r"(lo32(a[0])), "r"(hi32(a[0])), "r"(lo32(a[1])), "r"(hi32(a[1])),
-          "r"(lo32(b[0])), "r"(hi32(b[0])), "r"(lo32(b[1])), "r"(hi32(b[1])), "r"(cin));
-    (void)t;
-    r[0] = mk64(r0, r1); r[1] = mk64(r2, r3);
-}
-
-// two words, no carry in, no carry out (the whole pattern of the W = 2 class)
-__device__ __forceinline__ void add2_only(const uint64_t *a, const uint64_t *b, uint64_t *r) {
-    uint32_t r0, r1, r2, r3;
-    asm("{\n\t"
-        "add.cc.u32 %0, %4, %8;\n\t"
-        "addc.cc.u32 %1, %5, %9;\n\t"
-        "addc.cc.u32 %2, %6, %10;\n\t"
-        "addc.u32 %3, %7, %11;\n\t"
-        "}"
-        : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-        : "r"(lo32(a[0])), "r"(hi32(a[0])), "r"(lo32(a[1])), "r"(hi32(a[1])),
-          "r"(lo32(b[0])), "r"(hi32(b[0])), "r"(lo32(b[1])), "r"(hi32(b[1])));
-    r[0] = mk64(r0, r1); r[1] = mk64(r2, r3);
-}
-
-// one word with carry in and out
-__device__ __forceinline__ void add1(uint64_t a, uint64_t b, uint64_t &r, uint32_t cin, uint32_t &cout) {
-    uint32_t r0, r1, t;
-    asm("{\n\t"
-        "add.cc.u32 %3, %8, 0xffffffff;\n\t"
-        "addc.cc.u32 %0, %4, %6;\n\t"
-        "addc.cc.u32 %1, %5, %7;\n\t"
-        "addc.u32 %2, 0, 0;\n\t"
-        "}"
-        : "=r"(r0), "=r"(r1), "=r"(cout), "=r"(t)
-        : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)), "r"(cin));
-    r = mk64(r0, r1);
-}
-
-template <int W>
-__device__ __forceinline__ void add_words(const uint64_t (&a)[W], const uint64_t (&b)[W], uint64_t (&r)[W]) {
-    if (W == 1) {
-        r[0] = a[0] + b[0];
-    } else if (W == 2) {
-        add2_only(a, b, r);
-    } else {
-        uint32_t carry = 0;
-#pragma unroll
-        for (int x = 0; x + 2 <= W; x += 2) add2(a + x, b + x, r + x, carry, carry);
-        if (W & 1) add1(a[W - 1], b[W - 1], r[W - 1], carry, carry);
-    }
-}
-
-// LCS length of my pattern (masks in shared memory, column `pm`) and a text of n characters that
-// starts 8-byte aligned at `text` in shared memory.  Uniform over the CTA.
-template <int W>
-__device__ __forceinline__ uint32_t lcs_bitparallel(const uint64_t *__restrict__ pm, uint32_t nthr,
-                                                    const uint8_t *__restrict__ text, uint32_t n) {
-    uint64_t S[W];
-#pragma unroll
-    for (int x = 0; x < W; ++x) S[x] = ~0ull;
-    const uint2 *text8 = reinterpret_cast<const uint2 *>(text);
-    // byte addressing: the mask row of character c starts c * row_bytes after my column, so a
-    // character costs one byte extract (PRMT), one multiply-add and the load
-    const unsigned char *col = reinterpret_cast<const unsigned char *>(pm);
-    const uint32_t word_bytes = nthr * 8u, row_bytes = (uint32_t)W * word_bytes;
-    auto step = [&](uint32_t c) {
-        const unsigned char *row = col + c * row_bytes;
-        uint64_t M[W], u[W], sum[W];
-#pragma unroll
-        for (int x = 0; x < W; ++x) {
-            M[x] = *reinterpret_cast<const uint64_t *>(row + (uint32_t)x * word_bytes);
-            u[x] = S[x] & M[x];
-        }
-        add_words<W>(S, u, sum);
-        // u is a subset of S, so S - u == S & ~M: one three-input logic op per half instead of a
-        // subtract with borrow
-#pragma unroll
-        for (int x = 0; x < W; ++x) S[x] = sum[x] | (S[x] & ~M[x]);
-    };
-    uint32_t j = 0;
-    for (; j + 8 <= n; j += 8) {  // eight characters per shared-memory word
-        const uint2 w8 = text8[j >> 3];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) step(__byte_perm(w8.x, 0u, 0x4440u + q));
-#pragma unroll
-        for (int q = 0; q < 4; ++q) step(__byte_perm(w8.y, 0u, 0x4440u + q));
-    }
-    if (j < n) {
-        const uint2 w8 = text8[j >> 3];
-        for (uint32_t q = 0; j + q < n; ++q)
-            step(__byte_perm(q < 4 ? w8.x : w8.y, 0u, 0x4440u + (q & 3u)));
-    }
-    uint32_t lcs = 0;
-#pragma unroll
-    for (int x = 0; x < W; ++x) lcs += __popcll(~S[x]);
-    return lcs;
-}
-
-// Two texts against my pattern at once: the two S chains are independent, so their dependent
-// AND -> ADD -> OR sequences interleave and hide each other's latency (a CTA holds few warps when
-// the mask tables are large).  The texts run in lockstep over the length of the shorter one; the
-// rest of each is finished by itself.
-template <int W>
-__device__ __forceinline__ void lcs_bitparallel2(const uint64_t *__restrict__ pm, uint32_t nthr,
-                                                 const uint8_t *__restrict__ text_a, uint32_t na,
-                                                 const uint8_t *__restrict__ text_b, uint32_t nb,
-                                                 uint32_t &lcs_a, uint32_t &lcs_b) {
-    uint64_t Sa[W], Sb[W];
-#pragma unroll
-    for (int x = 0; x < W; ++x) Sa[x] = Sb[x] = ~0ull;
-    const uint2 *a8 = reinterpret_cast<const uint2 *>(text_a), *b8 = reinterpret_cast<const uint2 *>(text_b);
-    const unsigned char *col = reinterpret_cast<const unsigned char *>(pm);
-    const uint32_t word_bytes = nthr * 8u, row_bytes = (uint32_t)W * word_bytes;
-    auto step = [&](uint64_t (&S)[W], uint32_t c) {
-        const unsigned char *row = col + c * row_bytes;
-        uint64_t M[W], u[W], sum[W];
-#pragma unroll
-        for (int x = 0; x < W; ++x) {
-            M[x] = *reinterpret_cast<const uint64_t *>(row + (uint32_t)x * word_bytes);
-            u[x] = S[x] & M[x];
-        }
-        add_words<W>(S, u, sum);
-#pragma unroll
-        for (int x = 0; x < W; ++x) S[x] = sum[x] | (S[x] & ~M[x]);
-    };
-    const uint32_t nc = min(na, nb);
-    uint32_t j = 0;
-    for (; j + 8 <= nc; j += 8) {
-        const uint2 wa = a8[j >> 3], wb = b8[j >> 3];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            step(Sa, __byte_perm(wa.x, 0u, 0x4440u + q));
-            step(Sb, __byte_perm(wb.x, 0u, 0x4440u + q));
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            step(Sa, __byte_perm(wa.y, 0u, 0x4440u + q));
-            step(Sb, __byte_perm(wb.y, 0u, 0x4440u + q));
-        }
-    }
-    auto finish = [&](uint64_t (&S)[W], const uint2 *t8, uint32_t n) {
-        uint32_t i = j;
-        for (; i + 8 <= n; i += 8) {
-            const uint2 w8 = t8[i >> 3];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) step(S, __byte_perm(w8.x, 0u, 0x4440u + q));
-#pragma unroll
-            for (int q = 0; q < 4; ++q) step(S, __byte_perm(w8.y, 0u, 0x4440u + q));
-        }
-        if (i < n) {
-            const uint2 w8 = t8[i >> 3];
-            for (uint32_t q = 0; i + q < n; ++q)
-                step(S, __byte_perm(q < 4 ? w8.x : w8.y, 0u, 0x4440u + (q & 3u)));
-        }
-    };
-    finish(Sa, a8, na);
-    finish(Sb, b8, nb);
-    lcs_a = lcs_b = 0;
-#pragma unroll
-    for (int x = 0; x < W; ++x) { lcs_a += __popcll(~Sa[x]); lcs_b += __popcll(~Sb[x]); }
-}
-
-#ifndef Q_DUAL
-#define Q_DUAL 1   // score two left strings per round where the registers allow it (W <= 4)
-#endif
-
-// Reciprocals of the possible length sums (two strings of up to 64 * Q_MAX_WORDS characters).
-struct LenRcpTable {
-    double v[64 * Q_MAX_WORDS * 2 + 1];
-    constexpr LenRcpTable() : v() {
-        for (int u = 1; u <= 64 * Q_MAX_WORDS * 2; ++u) v[u] = 1.0 / (double)u;
-    }
-};
-__device__ const LenRcpTable g_len_rcp = LenRcpTable();
-
-// a / b as  q0 = RN(a * r);  q = fma(fma(-q0, b, a), r, q0)  with r = RN(1 / b).  For the operands
-// qratio_from_lcs feeds it this equals the correctly rounded quotient - every case is enumerated
-// by tests/csrc/fast_ratio_check.c - and it costs three float64 operations instead of the general
-// division sequence.
-__device__ __forceinline__ double div_by_rcp(double a, double b, double r) {
-    const double q0 = __dmul_rn(a, r);
-    return __fma_rn(__fma_rn(-q0, b, a), r, q0);
-}
-
-// QRatio(a, b) / 100 from the counts: 0 when either processed string is empty, else
-// ((1.0 - dist / lensum) * 100) / 100 with dist = lensum - 2 LCS — this exact operation order.
-__device__ __forceinline__ double qratio_from_lcs(uint32_t m, uint32_t n, uint32_t lcs) {
-    if (m == 0 || n == 0) return 0.0;
-    const uint32_t lensum = m + n, dist = lensum - 2u * lcs;
-    if (lensum <= 64u * Q_MAX_WORDS * 2u) {
-        const double norm_dist = div_by_rcp((double)dist, (double)lensum, g_len_rcp.v[lensum]);
-        const double norm_sim = __dsub_rn(1.0, norm_dist);
-        return div_by_rcp(__dmul_rn(norm_sim, 100.0), 100.0, 0.01);  // 0.01 is RN(1 / 100)
-    }
-    const double norm_dist = __ddiv_rn((double)dist, (double)lensum);
-    const double norm_sim = __dsub_rn(1.0, norm_dist);
-    return __ddiv_rn(__dmul_rn(norm_sim, 100.0), 100.0);
-}
 
 template <int W, bool LEVELS>
 __global__ void __launch_bounds__(Q_MAX_THREADS, 1)
@@ -333,7 +77,6 @@ qratio_allpairs_kernel(const QratioParams p) {
             if (p.job.cat_mode) rcat = __ldg(p.job.r_cat + r);
         }
         uint32_t cur_slot = 0xffffffffu, m = 0;
-        if (!LEVELS && kr) { m = build_masks(rg0); cur_slot = 0; }  // my columns only: no barrier needed
         if (LEVELS) {
             __syncthreads();  // s_misc of the previous unit consumed
             if (tid == 0) s_misc[0] = 0;
@@ -370,46 +113,7 @@ qratio_allpairs_kernel(const QratioParams p) {
             for (uint32_t i = tid; i < nl; i += nthr) s_cat[i] = p.job.cat_mode ? __ldg(p.job.l_cat + l0 + i) : 0;
             __syncthreads();
 
-            if (!LEVELS) {
-                // ---- one level per item: score and emit pair by pair ------------------------
-                auto emit_flat = [&](uint32_t li, uint32_t kl, uint32_t n, uint32_t lcs) {
-                    bool ok = r_valid && keep_categories(p.job.cat_mode, s_cat[li], rcat);
-                    double score = 0.0;
-                    if (kl && kr) {
-                        // flat: score_func(l0, r0); else compare_terms on K = 1 items: t = 1, weight 1/2
-                        score = qratio_from_lcs(m, n, lcs);
-                        if (!flat) score = __fma_rn(score, 0.5, 0.0);
-                        ++st_evals;
-                    }
-                    if (ok && (kl == 0) != (kr == 0)) {  // IndexError in the reference
-                        atomicOr(p.job.out_flags, NSM_FLAG_EMPTY_ITEM);
-                        ok = false;
-                    }
-                    emit_pairs(ok && score >= thr, l0 + li, r, score, static_cast<nsm_pair_t *>(p.job.out_pairs),
-                               p.job.out_capacity, count, p.job.out_flags);
-                };
-                // (uniform control flow; threads without a right level compute on stale masks, unused)
-                for (uint32_t li = 0; li < nl;) {
-                    const uint32_t lg0 = s_item_g0[li], kl = s_item_g0[li + 1] - lg0;
-                    const uint32_t n = kl ? s_lev_len[lg0] : 0u;
-                    if (Q_DUAL && W <= 4 && li + 1 < nl) {
-                        const uint32_t lg1 = s_item_g0[li + 1], kl1 = s_item_g0[li + 2] - lg1;
-                        if (kl && kl1) {
-                            const uint32_t n1 = s_lev_len[lg1];
-                            uint32_t lcs0, lcs1;
-                            lcs_bitparallel2<W>(pm, nthr, s_chr + s_lev_off[lg0], n, s_chr + s_lev_off[lg1], n1,
-                                                lcs0, lcs1);
-                            emit_flat(li, kl, n, lcs0);
-                            emit_flat(li + 1, kl1, n1, lcs1);
-                            li += 2;
-                            continue;
-                        }
-                    }
-                    const uint32_t lcs = kl ? lcs_bitparallel<W>(pm, nthr, s_chr + s_lev_off[lg0], n) : 0u;
-                    emit_flat(li, kl, n, lcs);
-                    ++li;
-                }
-            } else {
+            {
                 // ---- compare_terms' schedule as the outer loop, partial scores in smem --------
                 for (uint32_t li = 0; li < nl; ++li) s_acc[(size_t)li * nthr + tid] = 0.0;
                 uint32_t max_kl = 0;
@@ -476,8 +180,9 @@ qratio_allpairs_kernel(const QratioParams p) {
                         ok = false;
                     }
                     const double score = s_acc[(size_t)li * nthr + tid];
-                    emit_pairs(ok && score >= thr, l0 + li, r, score, static_cast<nsm_pair_t *>(p.job.out_pairs),
-                               p.job.out_capacity, count, p.job.out_flags);
+                    emit_pairs(ok && score >= thr, p.swap_out ? r : l0 + li, p.swap_out ? l0 + li : r, score,
+                               static_cast<nsm_pair_t *>(p.job.out_pairs), p.job.out_capacity, count,
+                               p.job.out_flags);
                 }
             }
         }
@@ -500,17 +205,103 @@ static int launch_qratio(const QratioParams &p, size_t smem, uint32_t grid, cuda
     return NSM_OK;
 }
 
-template <bool LEVELS>
-static int dispatch_qratio(uint32_t words, const QratioParams &p, size_t smem, uint32_t grid,
+static int dispatch_levels(uint32_t words, const QratioParams &p, size_t smem, uint32_t grid,
                            cudaStream_t stream) {
     switch (words) {
-        case 1: return launch_qratio<1, LEVELS>(p, smem, grid, stream);
-        case 2: return launch_qratio<2, LEVELS>(p, smem, grid, stream);
-        case 3: return launch_qratio<3, LEVELS>(p, smem, grid, stream);
-        case 4: return launch_qratio<4, LEVELS>(p, smem, grid, stream);
-        case 6: return launch_qratio<6, LEVELS>(p, smem, grid, stream);
-        default: return launch_qratio<8, LEVELS>(p, smem, grid, stream);
+        case 1: return launch_qratio<1, true>(p, smem, grid, stream);
+        case 2: return launch_qratio<2, true>(p, smem, grid, stream);
+        case 3: return launch_qratio<3, true>(p, smem, grid, stream);
+        case 4: return launch_qratio<4, true>(p, smem, grid, stream);
+        case 6: return launch_qratio<6, true>(p, smem, grid, stream);
+        default: return launch_qratio<8, true>(p, smem, grid, stream);
     }
+}
+
+// compare_terms over levels: the job's left rows x the right items [r_lo, r_hi) of the classes
+// <= Q_MAX_WORDS words.  left_max_len: longest level string among the job's left rows (sizes the
+// tile).  Returns NSM_ERR_UNSUPPORTED (without an error text) when one left item does not fit the
+// staged tile; the caller then takes the generic kernel for those rows.
+static int levels_launch(const nsm_strings_t *left, const nsm_strings_t *right, const nsm_job_t *job,
+                         uint32_t left_max_len, uint32_t r_lo, uint32_t r_hi, bool swap_out,
+                         cudaStream_t stream) {
+    if (job->l_row_end <= job->l_row_begin || r_hi <= r_lo) return NSM_OK;
+    const uint32_t kl = left->max_levels ? left->max_levels : 1u;
+    const uint32_t per_item_chr = kl * (((left_max_len ? left_max_len : 1u) + 7u) & ~7u);
+    uint32_t tl = (uint32_t)Q_TILE_LEVELS;
+    if (per_item_chr * tl > (uint32_t)Q_CHR_CAP) tl = (uint32_t)Q_CHR_CAP / per_item_chr;
+    if (kl * tl > (uint32_t)Q_LEV_CAP) tl = (uint32_t)Q_LEV_CAP / kl;
+    if (tl == 0) return NSM_ERR_UNSUPPORTED;
+
+    QratioParams p;
+    p.L = *left; p.R = *right; p.job = *job;
+    p.swap_out = swap_out ? 1u : 0u;
+    p.tile_left = tl;
+    p.n_alpha = left->n_alphabet ? left->n_alphabet : 1u;
+    const uint32_t n_rows = job->l_row_end - job->l_row_begin;
+    p.n_ltiles = (n_rows + tl - 1) / tl;
+    p.n_lgroups = (p.n_ltiles + Q_GROUP - 1) / Q_GROUP;
+
+    // one launch per word-count class of the right side (its items are stored class by class),
+    // each with the narrowest bit-vectors and as many threads as its mask tables leave room for
+    for (uint32_t w = 0; w < (uint32_t)Q_MAX_WORDS; ++w) {
+        p.r_begin = w ? right->class_end[w - 1] : 0u;
+        p.r_end = right->class_end[w];
+        if (p.r_begin < r_lo) p.r_begin = r_lo;
+        if (p.r_end > r_hi) p.r_end = r_hi;
+        if (p.r_end <= p.r_begin) continue;
+        const uint32_t words = w + 1;
+        // words actually instantiated: 1, 2, 3, 4, 6, 8
+        const uint32_t w_inst = words <= 4 ? words : (words <= 6 ? 6u : 8u);
+        uint32_t threads = Q_MAX_THREADS;
+        while (threads >= 32 && qratio_layout(p.n_alpha, w_inst, threads, tl, true).total > Q_SMEM_BUDGET)
+            threads -= 32;
+        if (threads < 32) {
+            set_error("alphabet %u x %u words does not fit shared memory", p.n_alpha, w_inst);
+            return NSM_ERR_BAD_ARG;
+        }
+        // no more threads than right items (rounded up to a warp): a small right side, e.g. one
+        // term against many synonyms, should not pay for idle mask columns
+        const uint32_t n_right = p.r_end - p.r_begin;
+        const uint32_t need = ((n_right + 31u) / 32u) * 32u;
+        if (threads > need) threads = need;
+        p.threads = threads;
+        const size_t smem = qratio_layout(p.n_alpha, w_inst, threads, tl, true).total;
+        p.n_rblocks = (n_right + threads - 1) / threads;
+        const uint64_t n_units = (uint64_t)p.n_lgroups * p.n_rblocks;
+        if (n_units > 0xffffffffull) {
+            set_error("too many work units (%llu); split the left row block", (unsigned long long)n_units);
+            return NSM_ERR_BAD_ARG;
+        }
+        const uint32_t resident = (uint32_t)sm_count();
+        const uint32_t grid = (uint32_t)(n_units < resident ? n_units : resident);
+        if (int rc = dispatch_levels(w_inst, p, smem, grid, stream)) return rc;
+    }
+    return NSM_OK;
+}
+
+// One direction of the product: `left` rows [row_lo, row_hi) x `right` items [r_lo, r_hi), all of
+// the right items within the classes <= 8 words (the pattern side of the per-thread kernels).
+static int short_pattern_pass(const nsm_strings_t *left, const nsm_strings_t *right, const nsm_job_t *job,
+                              uint32_t row_lo, uint32_t row_hi, uint32_t r_lo, uint32_t r_hi, bool levels,
+                              bool swap_out, cudaStream_t stream) {
+    if (row_hi <= row_lo || r_hi <= r_lo) return NSM_OK;
+    nsm_job_t j = *job;
+    j.l_row_begin = row_lo; j.l_row_end = row_hi;
+    if (swap_out) { j.l_cat = job->r_cat; j.r_cat = job->l_cat; }
+    if (!levels) return qratio_flat_launch(left, right, &j, r_lo, r_hi, swap_out, stream);
+    // left rows with level strings <= 512 characters are tiled for 512, the (few) others by the
+    // side's longest string; an item too large for the tile goes to the generic kernel
+    const uint32_t l_short = left->class_end[Q_MAX_WORDS - 1];
+    const uint32_t mid = row_lo > l_short ? row_lo : (row_hi < l_short ? row_hi : l_short);
+    j.l_row_end = mid;
+    const uint32_t cap = 64u * Q_MAX_WORDS;
+    int rc = levels_launch(left, right, &j, left->max_len < cap ? left->max_len : cap, r_lo, r_hi, swap_out, stream);
+    if (rc) return rc;
+    j.l_row_begin = mid; j.l_row_end = row_hi;
+    rc = levels_launch(left, right, &j, left->max_len, r_lo, r_hi, swap_out, stream);
+    if (rc == NSM_ERR_UNSUPPORTED)
+        rc = qratio_long_launch(left, right, &j, mid, row_hi, r_lo, r_hi, swap_out, stream);
+    return rc;
 }
 
 }  // namespace nsm
@@ -534,64 +325,35 @@ extern "C" int nsm_qratio_allpairs(const nsm_strings_t *left, const nsm_strings_
         set_error("both sides must be packed with one alphabet of <= 255 codes");
         return NSM_ERR_BAD_ARG;
     }
-    if (right->class_end[Q_MAX_WORDS - 1] != right->n_items) {
-        set_error("right level strings of up to %u characters; the kernel handles %d",
-                  right->max_len, 64 * Q_MAX_WORDS);
-        return NSM_ERR_UNSUPPORTED;
+    if (!left->level_hist || !right->level_hist) {
+        set_error("level_hist is missing (pack with gpu/pack.py:pack_strings)");
+        return NSM_ERR_BAD_ARG;
     }
+    for (int w = 1; w < Q_MAX_WORDS; ++w)
+        if (left->class_end[w] < left->class_end[w - 1] || right->class_end[w] < right->class_end[w - 1] ||
+            left->class_end[w] > left->n_items || right->class_end[w] > right->n_items) {
+            set_error("class_end must be non-decreasing and <= n_items");
+            return NSM_ERR_BAD_ARG;
+        }
     const bool levels = left->max_levels > 1 || right->max_levels > 1;
-    const uint32_t kl = left->max_levels ? left->max_levels : 1u;
-    const uint32_t per_item_chr = kl * (((left->max_len ? left->max_len : 1u) + 7u) & ~7u);
-    uint32_t tl = levels ? (uint32_t)Q_TILE_LEVELS : (uint32_t)Q_TILE_FLAT;
-    if (per_item_chr * tl > (uint32_t)Q_CHR_CAP) tl = (uint32_t)Q_CHR_CAP / per_item_chr;
-    if (kl * tl > (uint32_t)Q_LEV_CAP) tl = (uint32_t)Q_LEV_CAP / kl;
-    if (tl == 0) {
-        set_error("a left item (%u levels x %u characters) exceeds the staged tile", kl, left->max_len);
-        return NSM_ERR_UNSUPPORTED;
-    }
-
-    QratioParams p;
-    p.L = *left; p.R = *right; p.job = *job;
-    p.tile_left = tl;
-    p.n_alpha = left->n_alphabet ? left->n_alphabet : 1u;
-    const uint32_t n_rows = job->l_row_end - job->l_row_begin;
-    p.n_ltiles = (n_rows + tl - 1) / tl;
-    p.n_lgroups = (p.n_ltiles + Q_GROUP - 1) / Q_GROUP;
-
-    // one launch per word-count class of the right side (its items are stored class by class),
-    // each with the narrowest bit-vectors and as many threads as its mask tables leave room for
-    for (uint32_t w = 0; w < (uint32_t)Q_MAX_WORDS; ++w) {
-        p.r_begin = w ? right->class_end[w - 1] : 0u;
-        p.r_end = right->class_end[w];
-        if (p.r_end <= p.r_begin) continue;
-        const uint32_t words = w + 1;
-        // words actually instantiated: 1, 2, 3, 4, 6, 8
-        const uint32_t w_inst = words <= 4 ? words : (words <= 6 ? 6u : 8u);
-        uint32_t threads = Q_MAX_THREADS;
-        while (threads >= 32 && qratio_layout(p.n_alpha, w_inst, threads, tl, levels).total > Q_SMEM_BUDGET)
-            threads -= 32;
-        if (threads < 32) {
-            set_error("alphabet %u x %u words does not fit shared memory", p.n_alpha, w_inst);
-            return NSM_ERR_UNSUPPORTED;
-        }
-        // no more threads than right items (rounded up to a warp): a small right side, e.g. one
-        // term against many synonyms, should not pay for idle mask columns
-        const uint32_t n_right = p.r_end - p.r_begin;
-        const uint32_t need = ((n_right + 31u) / 32u) * 32u;
-        if (threads > need) threads = need;
-        p.threads = threads;
-        const size_t smem = qratio_layout(p.n_alpha, w_inst, threads, tl, levels).total;
-        p.n_rblocks = (n_right + threads - 1) / threads;
-        const uint64_t n_units = (uint64_t)p.n_lgroups * p.n_rblocks;
-        if (n_units > 0xffffffffull) {
-            set_error("too many work units (%llu); split the left row block", (unsigned long long)n_units);
-            return NSM_ERR_UNSUPPORTED;
-        }
-        const uint32_t resident = (uint32_t)sm_count();
-        const uint32_t grid = (uint32_t)(n_units < resident ? n_units : resident);
-        const int rc = levels ? dispatch_qratio<true>(w_inst, p, smem, grid, stream)
-                              : dispatch_qratio<false>(w_inst, p, smem, grid, stream);
-        if (rc) return rc;
+    // Items are stored by the length of their longest level string; those from class_end[7] on
+    // hold a string of more than 512 characters ("long").  The per-thread kernels keep the RIGHT
+    // item's string as the bit-vector pattern (<= 8 words); LCS is symmetric, so
+    //   all left rows   x short right items : as they are,
+    //   short left rows x long right items  : with the sides swapped (records are swapped back),
+    //   long left rows  x long right items  : one warp per pair (qratio_long.cu).
+    const uint32_t r_short = right->class_end[Q_MAX_WORDS - 1], l_short = left->class_end[Q_MAX_WORDS - 1];
+    const uint32_t lo = job->l_row_begin, hi = job->l_row_end;
+    const uint32_t l_short_hi = hi < l_short ? hi : l_short;      // short left rows of the block: [lo, l_short_hi)
+    const uint32_t l_long_lo = lo > l_short ? lo : l_short;       // long left rows: [l_long_lo, hi)
+    if (int rc = short_pattern_pass(left, right, job, lo, hi, 0u, r_short, levels, false, stream)) return rc;
+    if (r_short < right->n_items) {
+        if (int rc = short_pattern_pass(right, left, job, r_short, right->n_items, lo, l_short_hi, levels, true,
+                                        stream))
+            return rc;
+        if (l_long_lo < hi)
+            if (int rc = qratio_long_launch(left, right, job, l_long_lo, hi, r_short, right->n_items, false, stream))
+                return rc;
     }
     return NSM_OK;
 }

@@ -115,6 +115,7 @@ class Engine:
         self.last_infos: List[Dict] = []
         self.last_info: Dict = {}
         self._packer = None
+        self.trace: Optional[List[Tuple[float, str]]] = None   # set to [] to collect (host time, label)
 
     @property
     def device_packer(self):
@@ -163,7 +164,7 @@ class Engine:
             per_level = packed.level_sizes()
             kind = "sets"
         else:
-            st = nsmlib.NsmStrings(*[t.data_ptr() for t in tensors], packed.n_items,
+            st = nsmlib.NsmStrings(*[t.data_ptr() for t in tensors[:5]], packed.n_items,
                                    packed.n_levels, packed.max_levels, packed.max_len,
                                    packed.n_alphabet, 0,
                                    (C.c_uint32 * 8)(*[int(x) for x in packed.classes()]))
@@ -226,9 +227,16 @@ class Engine:
         with torch.cuda.device(self.device):
             return self._run_jobs(jobs, capacity, to_host, copy, decode)
 
+    def _mark(self, label: str) -> None:
+        if self.trace is not None:
+            import time
+
+            self.trace.append((time.perf_counter(), label))
+
     def _run_jobs(self, jobs: List["Job"], capacity: Optional[int], to_host: bool, copy: bool,
                   decode: bool = True):
         stream = torch.cuda.current_stream(self.device)
+        self._mark("run_jobs begin")
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
         copy_stream = self._copy_stream
@@ -351,6 +359,7 @@ class Engine:
                 slot ^= 1
             p_slot, p_item, p_done = pending
             p_done.synchronize()
+            self._mark(f"block done j{p_item['j']} rows {p_item['rb']}:{p_item['re']} mode {p_item['mode']}")
             words = ctl_pin[p_slot].numpy().view(np.uint64)
             count, flags = int(words[0]), int(words[1]) & 0xffffffff
             stats = [int(x) for x in words[2:2 + nsmlib.N_STATS]]
@@ -443,7 +452,9 @@ class Engine:
                 info["d2h_bytes"] += n_bytes + x_bytes
                 host_fill += n_bytes + x_bytes
             pending = nxt
+        self._mark("last block launched and counted")
         copy_stream.synchronize()
+        self._mark("copies done")
         for ev in slot_free:
             if ev is not None:
                 stream.wait_event(ev)

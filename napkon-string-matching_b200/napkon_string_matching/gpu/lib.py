@@ -82,7 +82,8 @@ class NsmSets(C.Structure):
 
 class NsmStrings(C.Structure):
     _fields_ = [("item_level_off", C.c_void_p), ("level_chr_off", C.c_void_p),
-                ("level_len", C.c_void_p), ("chr", C.c_void_p), ("n_items", C.c_uint32),
+                ("level_len", C.c_void_p), ("chr", C.c_void_p), ("level_hist", C.c_void_p),
+                ("n_items", C.c_uint32),
                 ("n_levels", C.c_uint32), ("max_levels", C.c_uint32), ("max_len", C.c_uint32),
                 ("n_alphabet", C.c_uint32), ("reserved_", C.c_uint32),
                 ("class_end", C.c_uint32 * 8)]

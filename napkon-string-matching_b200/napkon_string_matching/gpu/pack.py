@@ -147,6 +147,7 @@ class PackedStrings:
     max_len: int = 0
     perm: np.ndarray | None = None          # stored position -> original item index
     class_end: np.ndarray | None = None     # uint32[8]
+    level_hist: np.ndarray | None = None    # uint32[n_levels, 8]: 32 saturating byte counters
 
     @property
     def n_items(self) -> int:
@@ -162,7 +163,9 @@ class PackedStrings:
         return np.full(WORD_CLASSES, self.n_items, dtype=np.uint32)
 
     def arrays(self):
-        return [self.item_level_off, self.level_chr_off, self.level_len, self.chr]
+        if self.level_hist is None:
+            self.level_hist = string_histograms(self.level_chr_off, self.level_len, self.chr)
+        return [self.item_level_off, self.level_chr_off, self.level_len, self.chr, self.level_hist]
 
     def level_lengths(self) -> np.ndarray:
         return self.level_len.astype(np.int64)
@@ -186,7 +189,8 @@ class PackedStrings:
             (self.item_level_off[begin : end + 1] - np.uint32(g0)).astype(np.uint32),
             (self.level_chr_off[g0:g1] - np.uint32(c0)).astype(np.uint32),
             self.level_len[g0:g1].copy(), self.chr[c0:c1].copy(), self.n_alphabet, self.max_levels,
-            self.max_len, None if self.perm is None else self.perm[begin:end].copy(), cls)
+            self.max_len, None if self.perm is None else self.perm[begin:end].copy(), cls,
+            None if self.level_hist is None else self.level_hist[g0:g1].copy())
 
 
 def _pad_slots(a: np.ndarray) -> np.ndarray:
@@ -480,26 +484,60 @@ def fuzzy_level_strings(items_levels: Sequence[Sequence]) -> List[List[str]]:
              for level in lv] for lv in items_levels]
 
 
+def string_histograms(level_chr_off: np.ndarray, level_len: np.ndarray, chr_: np.ndarray) -> np.ndarray:
+    """uint32[n_levels, 8]: per level string 32 byte counters, saturating at 255, of its codes;
+    bucket = code & 31, counter of bucket b = byte (b & 3) of word b >> 2.  One insertion or deletion
+    changes one counter by one, so the L1 distance of two strings' counters is a lower bound of
+    their Indel distance (merging codes into buckets and saturating only lower it)."""
+    n_levels = len(level_len)
+    lens = level_len.astype(np.int64)
+    counts = np.zeros((n_levels, 32), dtype=np.int64)
+    if n_levels and lens.sum():
+        level_id = np.repeat(np.arange(n_levels, dtype=np.int64), lens)
+        src = np.repeat(level_chr_off.astype(np.int64), lens) + (
+            np.arange(int(lens.sum()), dtype=np.int64) - np.repeat(np.cumsum(lens) - lens, lens))
+        np.add.at(counts, (level_id, chr_[src].astype(np.int64) & 31), 1)
+    packed = np.minimum(counts, 255).astype(np.uint8).reshape(n_levels, 8, 4)
+    return np.ascontiguousarray(packed).view("<u4").reshape(n_levels, 8)
+
+
 def pack_strings(*sides: Sequence[Sequence[str]]) -> List[PackedStrings]:
-    """``sides[s][i][j]`` is the already processed string of level j of item i."""
+    """``sides[s][i][j]`` is the already processed string of level j of item i.
+
+    Alphabet: one code per code point while there are at most 255 of them.  Beyond that (two
+    sides): code points that occur on BOTH sides keep a code each; a code point that occurs on one
+    side only can never match anything of the other side, so all such code points of a side share
+    one code (the left side's and the right side's differ).  255 codes therefore cover any pair of
+    sides with at most 253 common code points."""
     per_side = []
     for s in sides:
         k = np.fromiter((len(lv) for lv in s), dtype=np.int64, count=len(s))
-        # order items by the 64-bit words their longest level needs (stable)
+        # order items by the length of their longest level (stable): lanes of a warp then hold
+        # patterns of nearly one length and a tile texts of nearly one length; the order is also
+        # the order by 64-bit words, which the kernels' word classes need
         longest = np.fromiter((max((len(x) for x in lv), default=0) for lv in s), dtype=np.int64,
                               count=len(s))
         words = np.minimum(np.maximum((longest + 63) // 64, 1), WORD_CLASSES + 1)
-        perm = np.argsort(words, kind="stable")
+        perm = np.argsort(longest, kind="stable")
         class_end = np.searchsorted(words[perm], np.arange(1, WORD_CLASSES + 1), side="right")
         strs = [x for i in perm for x in s[i]]
         lens = np.fromiter((len(x) for x in strs), dtype=np.int64, count=len(strs))
         cps = np.frombuffer("".join(strs).encode("utf-32-le"), dtype=np.uint32)
         per_side.append((k[perm], lens, cps, perm, class_end))
-    alphabet = np.unique(np.concatenate([c[2] for c in per_side])) if per_side else np.zeros(0)
-    if len(alphabet) > MAX_ALPHABET:
-        raise PackError(f"{len(alphabet)} distinct code points; the packed format allows 255")
-    out = []
-    for k, lens, cps, perm, class_end in per_side:
+    sets = [np.unique(c[2]) for c in per_side]
+    common = np.unique(np.concatenate(sets)) if sets else np.zeros(0, dtype=np.uint32)
+    one_sided = [False] * len(sets)
+    if len(common) > MAX_ALPHABET and len(sets) == 2:
+        # too many code points for one byte each: only those COMMON to both sides need a code of
+        # their own; all others of a side collapse onto one code of that side
+        common = np.intersect1d(sets[0], sets[1], assume_unique=True)
+        one_sided = [len(u) > len(common) for u in sets]
+    n_alphabet = len(common) + sum(one_sided)
+    if n_alphabet > MAX_ALPHABET:
+        raise PackError(f"{len(common)} code points are common to both sides; the packed format allows "
+                        f"{MAX_ALPHABET - 2}")
+    out, extra = [], len(common)
+    for (k, lens, cps, perm, class_end), own in zip(per_side, one_sided):
         item_level_off = np.zeros(len(k) + 1, dtype=np.int64)
         np.cumsum(k, out=item_level_off[1:])
         padded = _pad8(lens)
@@ -507,18 +545,24 @@ def pack_strings(*sides: Sequence[Sequence[str]]) -> List[PackedStrings]:
         np.cumsum(padded, out=level_chr_off[1:])
         if level_chr_off[-1] >= 2 ** 32:
             raise PackError("more than 4 GiB of level strings on one side")
-        codes = np.searchsorted(alphabet, cps).astype(np.uint8)
+        pos = np.searchsorted(common, cps)
+        hit = (pos < len(common)) & (common[np.minimum(pos, max(len(common) - 1, 0))] == cps) \
+            if len(common) else np.zeros(len(cps), dtype=bool)
+        codes = np.where(hit, pos, extra).astype(np.uint8)
+        if own:
+            extra += 1
         chr_ = np.zeros(int(level_chr_off[-1]), dtype=np.uint8)
         if len(codes):
             src_off = np.zeros(len(lens) + 1, dtype=np.int64)
             np.cumsum(lens, out=src_off[1:])
             dest = np.repeat(level_chr_off[:-1] - src_off[:-1], lens) + np.arange(len(codes), dtype=np.int64)
             chr_[dest] = codes
-        out.append(PackedStrings(item_level_off.astype(np.uint32), level_chr_off[:-1].astype(np.uint32),
-                                 lens.astype(np.uint32), chr_, int(len(alphabet)),
+        off32, len32 = level_chr_off[:-1].astype(np.uint32), lens.astype(np.uint32)
+        out.append(PackedStrings(item_level_off.astype(np.uint32), off32, len32, chr_, int(n_alphabet),
                                  int(k.max()) if len(k) else 0,
                                  int(lens.max()) if len(lens) else 0,
-                                 perm.astype(np.uint32), class_end.astype(np.uint32)))
+                                 perm.astype(np.uint32), class_end.astype(np.uint32),
+                                 string_histograms(off32, len32, chr_)))
     return out
 
 

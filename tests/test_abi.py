@@ -33,7 +33,7 @@ def test_struct_layouts_match_the_header():
     from napkon_string_matching.gpu import lib as nsmlib
 
     assert ctypes.sizeof(nsmlib.NsmSets) == 12 * 8 + 8 * 4
-    assert ctypes.sizeof(nsmlib.NsmStrings) == 4 * 8 + 6 * 4 + 8 * 4
+    assert ctypes.sizeof(nsmlib.NsmStrings) == 5 * 8 + 6 * 4 + 8 * 4
     assert nsmlib.NsmJob.threshold.offset == 16
     assert nsmlib.NsmJob.out_pairs.offset == 40
     assert ctypes.sizeof(nsmlib.NsmJob) == 120 and nsmlib.NsmJob.out_dict.offset == 88

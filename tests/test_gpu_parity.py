@@ -327,9 +327,10 @@ def test_jaccard_nested_levels_single_intersection_and_its_fallbacks(engine):
 
 
 def test_unsupported_inputs_raise_instead_of_falling_back(engine):
-    # a right-hand string longer than 512 characters: no kernel width for it
-    pl, pr = pack.pack_strings([["abc"]], [["x" * 600]])
-    with pytest.raises(nsmlib.NsmError, match="512|handles"):
+    # strings beyond 512 characters are scored (tests/test_gpu_fuzzy.py); what is refused: a level
+    # string beyond the generic kernel's 16384 characters on BOTH sides of a pair
+    pl, pr = pack.pack_strings([["ab" * 9000]], [["ba" * 9000]])
+    with pytest.raises(nsmlib.NsmError, match="exceed the generic kernel"):
         engine.all_pairs(engine.upload(pl), engine.upload(pr), 0.1, flat=True)
     # flat scoring needs one level per item
     pl, pr = pack.pack_sets([[["a"], ["b"]]], [[["a"]]])
