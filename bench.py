@@ -680,6 +680,8 @@ def measure(prep: Prepared, steps: int, warmup: int, rank: int, world: int, int_
     ms_e2e, (counts_e2e, d2h, packets, reruns, uncoded) = timed(prep.step_e2e, not self_flushing)
     barrier()
     t1 = time.time()
+    eng.time_kernels = False
+    e2e_kernel_ms, e2e_kernel_launches, e2e_launches = eng.kernel_ms, eng.kernel_launches_timed, eng.launches - launches0
     # host-side timeline of one more (untimed) end-to-end step: where the step's wall time goes
     eng.trace = []
     t_step = time.perf_counter()
@@ -688,8 +690,6 @@ def measure(prep: Prepared, steps: int, warmup: int, rank: int, world: int, int_
     timeline = [(round((t - t_step) * 1e3, 2), label) for t, label in eng.trace]
     timeline.append((round((time.perf_counter() - t_step) * 1e3, 2), "step returned"))
     eng.trace = None
-    eng.time_kernels = False
-    e2e_kernel_ms, e2e_kernel_launches, e2e_launches = eng.kernel_ms, eng.kernel_launches_timed, eng.launches - launches0
     if not separate_resident:
         ms, kernel_ms, kernel_launches, launches = e2e_kernel_ms, e2e_kernel_ms, e2e_kernel_launches, e2e_launches
         stats = {k: sum(i["stats"][k] for i in eng.last_infos) for k in eng.last_infos[0]["stats"]}

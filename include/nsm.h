@@ -197,6 +197,12 @@ int nsm_jaccard_allpairs(const nsm_sets_t *left, const nsm_sets_t *right, const 
 int nsm_qratio_allpairs(const nsm_strings_t *left, const nsm_strings_t *right, const nsm_job_t *job,
                         void *stream);
 
+/* Copies `bytes` (<= 256, a multiple of 8) of device memory to PINNED host memory with a one-warp
+ * kernel instead of the copy engine: the counters of a finished call (out_count, out_flags,
+ * out_stats) reach the host while a large record copy of an earlier call still occupies the
+ * device->host copy engine.  host_dst: page-locked host memory (device-accessible under UVA). */
+int nsm_publish(const void *dev_src, void *host_dst, uint32_t bytes, void *stream);
+
 /* Marks every slot of a score dictionary (NSM_OUT_CODED, uint64[NSM_DICT_SLOTS]) free. */
 int nsm_dict_reset(uint64_t *dict, void *stream);
 

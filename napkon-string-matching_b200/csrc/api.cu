@@ -96,3 +96,27 @@ extern "C" int nsm_dict_reset(uint64_t *dict, void *stream) {
                                    static_cast<cudaStream_t>(stream)));
     return NSM_OK;
 }
+
+namespace nsm {
+__global__ void publish_kernel(const unsigned long long *__restrict__ src, volatile unsigned long long *dst,
+                               uint32_t words) {
+    if (threadIdx.x < words) dst[threadIdx.x] = src[threadIdx.x];
+    __threadfence_system();
+}
+}  // namespace nsm
+
+extern "C" int nsm_publish(const void *dev_src, void *host_dst, uint32_t bytes, void *stream) {
+    using namespace nsm;
+    reset_launch_count();
+    if (!dev_src || !host_dst || bytes == 0 || bytes > 256 || (bytes & 7u) ||
+        (reinterpret_cast<uintptr_t>(dev_src) & 7u) || (reinterpret_cast<uintptr_t>(host_dst) & 7u)) {
+        set_error("nsm_publish: 8-byte aligned pointers and 8..256 bytes in multiples of 8");
+        return NSM_ERR_BAD_ARG;
+    }
+    publish_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const unsigned long long *>(dev_src), static_cast<volatile unsigned long long *>(host_dst),
+        bytes / 8);
+    count_launch();
+    NSM_CUDA_CHECK(cudaGetLastError());
+    return NSM_OK;
+}

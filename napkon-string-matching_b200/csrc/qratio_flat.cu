@@ -19,9 +19,9 @@
 //
 // Work decomposition: as in qratio.cu a thread owns one right item and keeps the pattern-match
 // masks of its string in shared memory, transposed [code][word][thread] (conflict-free).  A tile of
-// up to 64 left strings is staged in shared memory (padded with a code whose mask row is zero, so
+// up to 256 left strings is staged in shared memory (padded with a code whose mask row is zero, so
 // every string of the tile can be read to the tile's longest length without a predicate).  Phase 1
-// tests all tile x thread pairs with the bound and leaves a 64-bit survivor mask per thread.
+// tests all tile x thread pairs with the bound and leaves a survivor bit mask per thread.
 // Phase 2: every lane walks ITS OWN survivors, two at a time (two independent S chains), reading
 // its own text rows; the packer orders both sides by length, so the lanes of a warp hold patterns
 // of (nearly) one length, a tile holds texts of (nearly) one length, and survivor counts per lane
@@ -30,7 +30,10 @@
 
 namespace nsm {
 
-constexpr int QF_TILE = 64;
+constexpr int QF_TILE = 256;            // left strings per tile: survivor counts per lane even out
+constexpr int QF_MASK_WORDS = QF_TILE / 64;
+constexpr int QF_CHR_CAP = 32 * 1024;   // bytes of left strings staged per batch
+constexpr int QF_GROUP = 4;             // tiles per unit (one mask build per unit)
 
 struct QflatParams {
     nsm_strings_t L, R;
@@ -53,7 +56,7 @@ __host__ __device__ inline QflatLayout qflat_layout(uint32_t n_rows, uint32_t wo
     QflatLayout l;
     size_t o = 0;
     l.pm = o;   o += (size_t)n_rows * words * threads * 8;
-    l.chr = o;  o += Q_CHR_CAP;
+    l.chr = o;  o += QF_CHR_CAP;
     l.hist = o; o += QF_TILE * 32;
     l.cat = o;  o += QF_TILE * 8;
     l.len = o;  o += QF_TILE * 4;
@@ -174,8 +177,8 @@ qratio_flat_kernel(const QflatParams p) {
             }
         }
 
-        const uint32_t lt_begin = lgroup * Q_GROUP;
-        const uint32_t lt_end = min(lt_begin + (uint32_t)Q_GROUP, p.n_ltiles);
+        const uint32_t lt_begin = lgroup * QF_GROUP;
+        const uint32_t lt_end = min(lt_begin + (uint32_t)QF_GROUP, p.n_ltiles);
         for (uint32_t lt = lt_begin; lt < lt_end; ++lt) {
             const uint32_t t0 = p.job.l_row_begin + lt * QF_TILE;
             const uint32_t tn = min((uint32_t)QF_TILE, p.job.l_row_end - t0);
@@ -185,24 +188,21 @@ qratio_flat_kernel(const QflatParams p) {
                 if (tid == 0) s_misc[0] = 0;
                 __syncthreads();
                 // lengths first: they size the batch
-                uint32_t my_len = 0;
-                if (tid < tn - b0) {
-                    const uint32_t g0 = __ldg(p.L.item_level_off + t0 + b0 + tid);
-                    const uint32_t kl = __ldg(p.L.item_level_off + t0 + b0 + tid + 1) - g0;
-                    my_len = kl ? __ldg(p.L.level_len + g0) : 0xffffffffu;
-                    s_len[tid] = my_len;
+                uint32_t my_max = 0;
+                for (uint32_t i = tid; i < tn - b0; i += nthr) {
+                    const uint32_t g0 = __ldg(p.L.item_level_off + t0 + b0 + i);
+                    const uint32_t kl = __ldg(p.L.item_level_off + t0 + b0 + i + 1) - g0;
+                    const uint32_t len = kl ? __ldg(p.L.level_len + g0) : 0xffffffffu;
+                    s_len[i] = len;
+                    if (len != 0xffffffffu) my_max = max(my_max, len);
                 }
-                // (the first warps hold the tile's items: QF_TILE <= 64 <= blockDim rounded to warps)
-                if (tid < QF_TILE) {
-                    uint32_t v = my_len == 0xffffffffu ? 0u : my_len;
-                    v = __reduce_max_sync(FULL_MASK, v);
-                    if (lane == 0) atomicMax(&s_misc[0], v);
-                }
+                my_max = __reduce_max_sync(FULL_MASK, my_max);
+                if (lane == 0 && my_max) atomicMax(&s_misc[0], my_max);
                 __syncthreads();
                 const uint32_t longest = s_misc[0];
                 const uint32_t stride8 = (((longest + 7u) >> 3) + 1u) | 1u;  // odd: rows spread over the banks
                 const uint32_t stride = stride8 * 8u;
-                uint32_t bn = min(tn - b0, (uint32_t)Q_CHR_CAP / stride - 1u);  // one row is the all-padding dummy
+                uint32_t bn = min(tn - b0, (uint32_t)QF_CHR_CAP / stride - 1u);  // one row is the all-padding dummy
                 if (bn == 0) { __trap(); }  // the host checked that one string fits
                 // batch b0 .. b0+bn: texts (padded), counters, category masks
                 for (uint32_t idx = tid; idx < (bn + 1) * stride8; idx += nthr) {
@@ -233,24 +233,34 @@ qratio_flat_kernel(const QflatParams p) {
                 const uint32_t l0 = t0 + b0;
 
                 // ---- phase 1: the distance bound, all pairs of the batch ----------------------
-                uint64_t mask = 0;
+                uint64_t mask[QF_MASK_WORDS];
+#pragma unroll
+                for (int x = 0; x < QF_MASK_WORDS; ++x) mask[x] = 0;
                 bool special = false;
-                for (uint32_t li = 0; li < bn; ++li) {
-                    const uint32_t n = s_len[li];
-                    const uint4 a = reinterpret_cast<const uint4 *>(s_hist)[2 * li];
-                    const uint4 b = reinterpret_cast<const uint4 *>(s_hist)[2 * li + 1];
-                    uint32_t d1 = sad4(a.x, hr[0], 0u);
-                    d1 = sad4(a.y, hr[1], d1); d1 = sad4(a.z, hr[2], d1); d1 = sad4(a.w, hr[3], d1);
-                    d1 = sad4(b.x, hr[4], d1); d1 = sad4(b.y, hr[5], d1); d1 = sad4(b.z, hr[6], d1);
-                    d1 = sad4(b.w, hr[7], d1);
-                    const bool both = n != 0xffffffffu && kr != 0;
-                    const bool pass = r_valid && both && keep_categories(p.job.cat_mode, s_cat[li], rcat) &&
-                                      (int)d1 <= (int)s_dmax[both ? m + n : 0u];
-                    mask |= (uint64_t)pass << li;
-                    special |= (n == 0xffffffffu) || kr == 0;
+                uint32_t n_pass = 0;
+#pragma unroll
+                for (int x = 0; x < QF_MASK_WORDS; ++x) {
+                    uint64_t word = 0;
+                    const uint32_t li_end = min(bn, 64u * (x + 1));
+                    for (uint32_t li = 64u * x; li < li_end; ++li) {
+                        const uint32_t n = s_len[li];
+                        const uint4 a = reinterpret_cast<const uint4 *>(s_hist)[2 * li];
+                        const uint4 b = reinterpret_cast<const uint4 *>(s_hist)[2 * li + 1];
+                        uint32_t d1 = sad4(a.x, hr[0], 0u);
+                        d1 = sad4(a.y, hr[1], d1); d1 = sad4(a.z, hr[2], d1); d1 = sad4(a.w, hr[3], d1);
+                        d1 = sad4(b.x, hr[4], d1); d1 = sad4(b.y, hr[5], d1); d1 = sad4(b.z, hr[6], d1);
+                        d1 = sad4(b.w, hr[7], d1);
+                        const bool both = n != 0xffffffffu && kr != 0;
+                        const bool pass = r_valid && both && keep_categories(p.job.cat_mode, s_cat[li], rcat) &&
+                                          (int)d1 <= (int)s_dmax[both ? m + n : 0u];
+                        word |= (uint64_t)pass << (li & 63u);
+                        special |= (n == 0xffffffffu) || kr == 0;
+                    }
+                    mask[x] = word;
+                    n_pass += __popcll(word);
                 }
                 st_bound += r_valid ? bn : 0u;
-                st_cand += __popcll(mask);
+                st_cand += n_pass;
                 // items without a level (K == 0): both empty -> compare_terms returns 0; one -> IndexError
                 if (__any_sync(FULL_MASK, special)) {
                     for (uint32_t li = 0; li < bn; ++li) {
@@ -263,10 +273,22 @@ qratio_flat_kernel(const QflatParams p) {
                 }
 
                 // ---- phase 2: every lane scores its own survivors, two per round ------------------
-                while (__any_sync(FULL_MASK, mask != 0)) {
-                    uint32_t li0 = bn, li1 = bn;   // bn: the dummy row
-                    if (mask) { li0 = __ffsll((long long)mask) - 1; mask &= mask - 1; }
-                    if (mask) { li1 = __ffsll((long long)mask) - 1; mask &= mask - 1; }
+                auto next_survivor = [&]() -> uint32_t {   // my lowest survivor, removed; bn (the dummy row): none
+                    uint32_t pick = bn;
+                    bool found = false;
+#pragma unroll
+                    for (int x = 0; x < QF_MASK_WORDS; ++x) {   // branch-free: the words stay in registers
+                        const bool take = !found && mask[x] != 0;
+                        const uint32_t b = (uint32_t)__ffsll((long long)mask[x]) - 1u;
+                        pick = take ? 64u * x + b : pick;
+                        mask[x] = take ? (mask[x] & (mask[x] - 1)) : mask[x];
+                        found |= take;
+                    }
+                    return pick;
+                };
+                while (__any_sync(FULL_MASK, n_pass != 0)) {
+                    const uint32_t li0 = next_survivor(), li1 = next_survivor();
+                    n_pass -= min(n_pass, 2u);
                     const uint32_t n0 = li0 < bn ? s_len[li0] : 0u, n1 = li1 < bn ? s_len[li1] : 0u;
                     const uint32_t trip = __reduce_max_sync(FULL_MASK, max(n0, n1));
                     const uint2 *ta = reinterpret_cast<const uint2 *>(s_chr + li0 * stride);
@@ -343,10 +365,10 @@ int qratio_flat_launch(const nsm_strings_t *left, const nsm_strings_t *right, co
     p.n_rows = (left->n_alphabet ? left->n_alphabet : 1u) + 1u;
     const uint32_t n_rows_l = job->l_row_end - job->l_row_begin;
     p.n_ltiles = (n_rows_l + QF_TILE - 1) / QF_TILE;
-    p.n_lgroups = (p.n_ltiles + Q_GROUP - 1) / Q_GROUP;
+    p.n_lgroups = (p.n_ltiles + QF_GROUP - 1) / QF_GROUP;
     const uint64_t table_len = (uint64_t)left->max_len + 64ull * Q_MAX_WORDS + 1ull;
     const uint32_t row_bytes = ((((left->max_len + 7u) >> 3) + 1u) | 1u) * 8u;
-    if (2u * row_bytes > (uint32_t)Q_CHR_CAP || table_len > 32768) {
+    if (2u * row_bytes > (uint32_t)QF_CHR_CAP || table_len > 32768) {
         set_error("a left level string of %u characters exceeds the staged tile", left->max_len);
         return NSM_ERR_UNSUPPORTED;
     }
@@ -360,15 +382,14 @@ int qratio_flat_launch(const nsm_strings_t *left, const nsm_strings_t *right, co
         const uint32_t words = w + 1;
         const uint32_t w_inst = words <= 4 ? words : (words <= 6 ? 6u : 8u);
         uint32_t threads = Q_MAX_THREADS;
-        while (threads >= 64 && qflat_layout(p.n_rows, w_inst, threads, p.table_len).total > Q_SMEM_BUDGET)
+        while (threads >= 32 && qflat_layout(p.n_rows, w_inst, threads, p.table_len).total > Q_SMEM_BUDGET)
             threads -= 32;
-        if (threads < 64) {
+        if (threads < 32) {
             set_error("alphabet %u x %u words does not fit shared memory", p.n_rows - 1, w_inst);
             return NSM_ERR_UNSUPPORTED;
         }
         const uint32_t n_right = p.r_end - p.r_begin;
-        uint32_t need = ((n_right + 31u) / 32u) * 32u;
-        if (need < 64u) need = 64u;   // the first QF_TILE threads stage the tile
+        const uint32_t need = ((n_right + 31u) / 32u) * 32u;
         if (threads > need) threads = need;
         p.threads = threads;
         const size_t smem = qflat_layout(p.n_rows, w_inst, threads, p.table_len).total;

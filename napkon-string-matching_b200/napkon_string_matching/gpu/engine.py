@@ -91,7 +91,7 @@ class Records:
 
 
 class Engine:
-    PIPELINE_BLOCK_BYTES = 512 << 20
+    PIPELINE_BLOCK_BYTES = 160 << 20   # record bytes per row block: the last block's copy-out is exposed
     PIPELINE_MIN_PAIRS = 1 << 26   # smaller jobs are one launch: a probe costs more than it saves
 
     def __init__(self, device: Optional[int] = None, max_pairs_per_block: int = 1 << 30):
@@ -319,7 +319,11 @@ class Engine:
                 e1.record(stream)
                 self._timed.append((e0, e1))
             self.launches += self.lib.nsm_last_launch_count()
-            ctl_pin[slot].copy_(c, non_blocking=True)
+            # the counters go to the host through a one-warp kernel, not the copy engine: a 64-byte
+            # copy would queue behind the record copy of the previous block (milliseconds)
+            nsmlib.check(self.lib.nsm_publish(c.data_ptr(), ctl_pin[slot].data_ptr(), 64,
+                                              C.c_void_p(stream.cuda_stream)))
+            self.launches += 1
             done = torch.cuda.Event()
             done.record(stream)
             return done

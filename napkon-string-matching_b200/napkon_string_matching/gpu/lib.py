@@ -68,7 +68,7 @@ PACK_FLAG_TOO_LARGE, PACK_FLAG_NOT_NESTED, PACK_FLAG_BAD_ID = 1, 2, 4
 
 EXPORTS = ("nsm_version", "nsm_last_error", "nsm_last_launch_count", "nsm_jaccard_allpairs",
            "nsm_qratio_allpairs", "nsm_microbench", "nsm_pack_count_ids", "nsm_pack_scratch_bytes",
-           "nsm_pack_sets_measure", "nsm_pack_sets_fill", "nsm_dict_reset")
+           "nsm_pack_sets_measure", "nsm_pack_sets_fill", "nsm_dict_reset", "nsm_publish")
 
 
 class NsmSets(C.Structure):
@@ -130,6 +130,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(first), C.POINTER(first), C.POINTER(NsmJob), C.c_void_p]
+    lib.nsm_publish.restype = C.c_int
+    lib.nsm_publish.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
     lib.nsm_dict_reset.restype = C.c_int
     lib.nsm_dict_reset.argtypes = [C.c_void_p, C.c_void_p]
     lib.nsm_microbench.restype = C.c_int

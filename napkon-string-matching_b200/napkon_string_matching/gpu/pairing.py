@@ -147,25 +147,31 @@ def upload_levels(engine, left_levels, right_levels, score_func: str):
     builds the packed arrays (gpu/device_pack.py).  An item beyond the device packer's per-item
     limit sends the comparison through the numpy packer instead.  Strings are packed on the host
     (their per-level ``default_process`` is Python string work)."""
+    from napkon_string_matching.gpu.stages import stage
+
     packer = getattr(engine, "device_packer", None) if KINDS[score_func] == "sets" else None
     if packer is not None:
         from napkon_string_matching.gpu.device_pack import RawSets
 
-        parts = [pack._csr_from_nested(s) for s in (left_levels, right_levels)]
-        tokens = [t for _, _, flat in parts for t in flat]
-        codes, uniques = pd.factorize(np.asarray(tokens, dtype=object)) if tokens else (np.zeros(0, np.int64), [])
-        raws, pos = [], 0
-        for item_level_off, level_off, flat in parts:
-            raws.append(RawSets(item_level_off.astype(np.uint32), level_off.astype(np.uint32),
-                                codes[pos:pos + len(flat)].astype(np.uint32), nsmlib.RAW_LEVELS))
-            pos += len(flat)
+        with stage("token codes (factorize)"):
+            parts = [pack._csr_from_nested(s) for s in (left_levels, right_levels)]
+            tokens = [t for _, _, flat in parts for t in flat]
+            codes, uniques = pd.factorize(np.asarray(tokens, dtype=object)) if tokens else (np.zeros(0, np.int64), [])
+            raws, pos = [], 0
+            for item_level_off, level_off, flat in parts:
+                raws.append(RawSets(item_level_off.astype(np.uint32), level_off.astype(np.uint32),
+                                    codes[pos:pos + len(flat)].astype(np.uint32), nsmlib.RAW_LEVELS))
+                pos += len(flat)
         try:
-            dl, dr = packer.pack(raws, len(uniques), rank="frequency")
+            with stage("H2D + device packing"):
+                dl, dr = packer.pack(raws, len(uniques), rank="frequency")
             return dl, dr, (None, None)
         except pack.PackTooLarge:
             pass   # the numpy packer below has no per-item limit
-    pl, pr = pack_levels(left_levels, right_levels, score_func)
-    return engine.upload(pl), engine.upload(pr), (getattr(pl, "perm", None), getattr(pr, "perm", None))
+    with stage("host packing (numpy)"):
+        pl, pr = pack_levels(left_levels, right_levels, score_func)
+    with stage("H2D"):
+        return engine.upload(pl), engine.upload(pr), (getattr(pl, "perm", None), getattr(pr, "perm", None))
 
 
 def score_all_pairs(left_levels, right_levels, score_func: str, score_threshold: float,
@@ -197,7 +203,10 @@ def score_all_pairs(left_levels, right_levels, score_func: str, score_threshold:
             return (ml & mr) == 0
         return False
 
-    bad = first_raising_pair(left_levels, right_levels, jaccard, excluded)
+    from napkon_string_matching.gpu.stages import stage
+
+    with stage("scan for pairs the reference raises on"):
+        bad = first_raising_pair(left_levels, right_levels, jaccard, excluded)
     if bad is not None:
         exc, li, ri = bad
         if exc is IndexError:
@@ -216,9 +225,10 @@ def score_all_pairs(left_levels, right_levels, score_func: str, score_threshold:
             lmask, rmask = lmask[lperm], rmask[rperm]
         kw = dict(l_cat=engine.upload_masks(lmask), r_cat=engine.upload_masks(rmask),
                   cat_mode=categories["cat_mode"])
-    records = distributed.sharded_all_pairs(
-        lambda b, e: engine.all_pairs(dl, dr, score_threshold, rows=(b, e), **kw),
-        dl.weights)
+    with stage("kernels + D2H + decode (engine)"):
+        records = distributed.sharded_all_pairs(
+            lambda b, e: engine.all_pairs(dl, dr, score_threshold, rows=(b, e), **kw),
+            dl.weights)
     # pairs the reference never scores (excluded before the loop) may carry the kernel's flags;
     # anything else was ruled out by first_raising_pair above
     if host_cat is not None and len(records):
@@ -226,8 +236,9 @@ def score_all_pairs(left_levels, right_levels, score_func: str, score_threshold:
                             for l, r in zip(records["left"], records["right"])), dtype=bool,
                            count=len(records))
         records = records[keep]
-    order = np.lexsort((records["right"], records["left"]))
-    return records[order]
+    with stage("sort records"):
+        order = np.lexsort((records["right"], records["left"]))
+        return records[order]
 
 
 def not_blocked(records: np.ndarray, left_ids: Sequence, right_ids: Sequence, blocked: set

@@ -145,9 +145,12 @@ class ComparableData(Data):
                 cache_file.parent.mkdir(parents=True, exist_ok=True)
                 logger.info("write cache to file")
                 # a reader never sees a half-written file: write aside, then rename
+                from napkon_string_matching.gpu.stages import stage
+
                 tmp = cache_file.with_name(f"{cache_file.name}.{os.getpid()}.tmp")
-                result.write_json(tmp)
-                os.replace(tmp, cache_file)
+                with stage("cache JSON"):
+                    result.write_json(tmp)
+                    os.replace(tmp, cache_file)
 
         # outside of the caching, so one cache serves several thresholds
         result = result[result.match_score >= score_threshold]
@@ -177,6 +180,7 @@ class ComparableData(Data):
         **kwargs,
     ) -> Comparable:
         from napkon_string_matching.gpu import pairing
+        from napkon_string_matching.gpu.stages import stage
 
         # unknown names fail exactly like the reference's getattr (comparable_data.py:150)
         getattr(napkon_string_matching.compare.score_functions, score_func)
@@ -192,8 +196,9 @@ class ComparableData(Data):
 
         left_df, right_df = left.map_for_comparable(), right.map_for_comparable()
         term = ComparableColumns.TERM.value
-        left_levels = [self.gen_comp_value(item) for item in left_df[compare_column]]
-        right_levels = [self.gen_comp_value(item) for item in right_df[compare_column]]
+        with stage("tokenise (gen_comp_value)"):
+            left_levels = [self.gen_comp_value(item) for item in left_df[compare_column]]
+            right_levels = [self.gen_comp_value(item) for item in right_df[compare_column]]
         left_df = left_df.assign(**{QUESTION_OUTPUT: [":".join(flatten_list(t)) for t in left_df[term]]})
         right_df = right_df.assign(**{QUESTION_OUTPUT: [":".join(flatten_list(t)) for t in right_df[term]]})
 
@@ -220,7 +225,8 @@ class ComparableData(Data):
             logger.info("removed %i black-listed pairs", int((~keep).sum()))
             records = records[keep]
 
-        frame = pairing.result_frame(records, left_df, right_df, left_prefix, right_prefix)
+        with stage("result frame"):
+            frame = pairing.result_frame(records, left_df, right_df, left_prefix, right_prefix)
         logger.info("got %s entries", "{:,}".format(len(frame)))
         return Comparable(data=frame, left_name=left_prefix, right_name=right_prefix)
 

@@ -494,3 +494,78 @@ def test_jaccard_two_bit_filter_with_folded_shared_ids(engine):
     pl, pr = fs.folded_pair_packs()
     out, info = check_against_oracle(engine, pl, pr, 0.5)
     assert len(out) == 1 and info["flags"] == 0
+
+
+def test_definitions_1m_x_20k_full_size(engine):
+    """BASELINE configs[3] at full size: 1M cohort items x 20k GECCO/KDS-style definitions
+    (Term-shaped token sets, K <= 3), thr 0.5, packed on the device.  Size-independent checks:
+    every kept score is the oracle's; the thr-0.5 set is the thr-0.45 set cut at 0.5; two
+    sub-blocks (the first rows and rows around the middle) are enumerated completely by the
+    oracle."""
+    from napkon_string_matching.gpu import device_pack as dp
+
+    L = syn.term_level_sets(1_000_000, syn.SEED_LEFT)
+    R = syn.definition_level_sets(20_000, syn.SEED_DEFS)
+    dl, dr = engine.device_packer.pack([dp.raw_from_parts(*L), dp.raw_from_parts(*R)], 20000, rank="frequency")
+    hi = engine.all_pairs(dl, dr, 0.5)
+    assert engine.last_info["flags"] == 0 and len(hi) > 1000
+    lo = engine.all_pairs(dl, dr, 0.45)
+    khi, shi = _keyed(hi, dr.n_items)
+    klo, slo = _keyed(lo, dr.n_items)
+    assert len(khi) == len(np.unique(khi))
+    sel = slo >= 0.5
+    assert np.array_equal(klo[sel], khi) and np.array_equal(slo[sel].view(np.uint64), shi.view(np.uint64))
+    # the oracle works on host packs with the SAME id ranking the device used
+    rank = engine.device_packer.last_rank
+    pl, pr = pack.pack_part_id_sets(*L, 20000, rank), pack.pack_part_id_sets(*R, 20000, rank)
+    want, _ = c_oracle.score_pairs(pl, pr, lo["left"], lo["right"])
+    assert np.array_equal(want.view(np.uint64), lo["score"].view(np.uint64))
+    for b0, b1 in ((0, 3000), (499_000, 502_000)):
+        sub, _ = c_oracle.all_pairs(pl, pr, 0.45, l_begin=b0, l_end=b1)
+        in_block = (lo["left"] >= b0) & (lo["left"] < b1)
+        assert_same_triples((lo["left"][in_block], lo["right"][in_block], lo["score"][in_block]),
+                            (sub["left"], sub["right"], sub["score"]))
+
+
+def test_term_1m_x_1m_sampled_properties(engine):
+    """BASELINE configs[4] at full size (1M x 1M Term items, thr 0.5; about 6 s of kernel time):
+    kept scores equal the oracle's, no pair is kept twice, a random sample of 2e5 pairs is kept
+    exactly when the oracle scores it >= 0.5, and a 2000 x 2000 sub-block is enumerated by the
+    oracle.  Skipped when the GPU has less than 40 GB free."""
+    import time
+
+    import torch
+
+    from napkon_string_matching.gpu import device_pack as dp
+
+    if torch.cuda.mem_get_info()[0] < 40 << 30:
+        pytest.skip("needs 40 GB of free device memory")
+    n = 1_000_000
+    L, R = syn.term_level_sets(n, syn.SEED_LEFT), syn.term_level_sets(n, syn.SEED_RIGHT)
+    dl, dr = engine.device_packer.pack([dp.raw_from_parts(*L), dp.raw_from_parts(*R)], 20000, rank="frequency")
+    t0 = time.perf_counter()
+    rec = engine.all_pairs(dl, dr, 0.5)
+    assert time.perf_counter() - t0 < 60, "1M x 1M took more than a minute"
+    assert engine.last_info["flags"] == 0 and engine.last_info["reruns"] == 0
+    key, score = _keyed(rec, n)
+    assert len(key) == len(np.unique(key)) and len(key) > 100_000
+    rank = engine.device_packer.last_rank
+    pl, pr = pack.pack_part_id_sets(*L, 20000, rank), pack.pack_part_id_sets(*R, 20000, rank)
+    want, _ = c_oracle.score_pairs(pl, pr, rec["left"], rec["right"])
+    assert np.array_equal(want.view(np.uint64), rec["score"].view(np.uint64))
+    rng = np.random.default_rng(5)
+    li = rng.integers(0, n, size=200_000).astype(np.uint32)
+    ri = rng.integers(0, n, size=200_000).astype(np.uint32)
+    # random pairs almost never reach 0.5: add pairs around kept ones (same left, neighbouring right)
+    li = np.concatenate([li, rec["left"][:50_000], rec["left"][:50_000]])
+    ri = np.concatenate([ri, rec["right"][:50_000], (rec["right"][:50_000] + 1) % n]).astype(np.uint32)
+    probe = li.astype(np.uint64) * np.uint64(n) + ri
+    pos = np.searchsorted(key, probe)
+    kept = (pos < len(key)) & (key[np.minimum(pos, len(key) - 1)] == probe)
+    got, _ = c_oracle.score_pairs(pl, pr, li, ri)
+    assert np.array_equal(got >= 0.5, kept)
+    b0 = 700_000
+    sub, _ = c_oracle.all_pairs(pl, pr.rows(0, 2000), 0.5, l_begin=b0, l_end=b0 + 2000)
+    in_block = (rec["left"] >= b0) & (rec["left"] < b0 + 2000) & (rec["right"] < 2000)
+    assert_same_triples((rec["left"][in_block], rec["right"][in_block], rec["score"][in_block]),
+                        (sub["left"], sub["right"], sub["score"]))
