@@ -72,6 +72,10 @@ WORKLOADS = {
                      desc="fuzzy_match flat strings 20k x 20k, avg 60 chars, thr 0.7"),
     "fuzzy200k": dict(kind="fuzzy", n=200_000, thr=0.7,
                       desc="cfg3: fuzzy_match flat strings 200k x 200k, avg 60 chars, thr 0.7"),
+    "mesh50k": dict(kind="mesh", n=50_000, n_right=300_000, thr=0.85,
+                    desc="token enrichment (SURVEY 8 f1, MeshProvider.get_matches for a whole cohort): 50k item "
+                         "terms x 300k MeSH-style synonyms, flat fuzzy_match, tokens.score_threshold 0.85"),
+    "mesh5k": dict(kind="mesh", n=5_000, n_right=30_000, thr=0.85, desc="reduced mesh (debug)"),
     "fuzzyterm10k": dict(kind="fuzzyterm", n=10_000, thr=0.5,
                          desc="the reference's shipped config: fuzzy_match on Term (K 2-4 levels), "
                               "10k x 10k items, cache_threshold 0.5"),
@@ -129,6 +133,30 @@ def build_fuzzy(n: int, rank: int):
     return {"left": pl, "right": pr}, {"left": sl, "right": sr}, [("left", "right")]
 
 
+def build_mesh(wl: dict, rank: int):
+    """Left: what get_matches scores for an item, " ".join(Term) (header, question, parameter);
+    right: synonym terms of 1-4 words."""
+    from napkon_string_matching import synthetic as syn
+    from napkon_string_matching.gpu import pack
+    from napkon_string_matching.text.process import default_process
+
+    vocab = syn.vocabulary()
+    rng = np.random.default_rng(syn.SEED_LEFT + 1000 * rank)
+    body = syn._Drawer(rng, vocab, syn.zipf_probs(len(vocab)))
+    head = syn._Drawer(rng, vocab[:400], syn.zipf_probs(400))
+    terms = []
+    for _ in range(wl["n"]):
+        u = rng.random()
+        parts = [head.text(2) for _ in range(0 if u < 0.4 else (1 if u < 0.7 else 2))]
+        parts += [body.text(int(rng.integers(3, 10))), body.text(int(rng.integers(1, 6)))]
+        terms.append([default_process(" ".join(parts))])
+    rng = np.random.default_rng(syn.SEED_DEFS + 1000 * rank)
+    words = syn._Drawer(rng, vocab, syn.zipf_probs(len(vocab)))
+    synonyms = [[default_process(words.text(int(rng.integers(1, 5))))] for _ in range(wl["n_right"])]
+    pl, pr = pack.pack_strings(terms, synonyms)
+    return {"left": pl, "right": pr}, {"left": terms, "right": synonyms}, [("left", "right")]
+
+
 def build_fuzzyterm(n: int, rank: int):
     """Term items as strings: per level the joined, processed token string QRatio sees."""
     from napkon_string_matching import synthetic as syn
@@ -183,6 +211,8 @@ def build_workload(wl: dict, rank: int):
         return build_tokenids(wl["n"], rank)
     if wl["kind"] == "term":
         return build_term(wl, rank)
+    if wl["kind"] == "mesh":
+        return build_mesh(wl, rank)
     return build_fuzzy(wl["n"], rank)
 
 
@@ -336,7 +366,7 @@ def cpu_port(workload: dict, raw, pairs, seconds: float, procs: int, packs=None)
     import multiprocessing as mp
 
     a, b = pairs[0]
-    if workload["kind"] in ("fuzzy", "fuzzyterm"):
+    if workload["kind"] in ("fuzzy", "fuzzyterm", "mesh"):
         from oracle import c_oracle
 
         os.environ["OMP_NUM_THREADS"] = str(procs)
@@ -347,7 +377,7 @@ def cpu_port(workload: dict, raw, pairs, seconds: float, procs: int, packs=None)
         while time.perf_counter() - t_start < seconds:
             i = n_blocks % avail
             blk = left.rows(i * rows_per_block, min(left.n_items, (i + 1) * rows_per_block))
-            c_oracle.all_pairs(blk, right, workload["thr"], flat=workload["kind"] == "fuzzy")
+            c_oracle.all_pairs(blk, right, workload["thr"], flat=workload["kind"] != "fuzzyterm")
             done_pairs += int(np.maximum.outer(blk.levels_per_item(), right.levels_per_item()).sum())
             n_blocks += 1
         wall = time.perf_counter() - t_start
@@ -459,7 +489,7 @@ def cpu_reference(workload: dict, raw, pairs, seconds: float, procs: int, packs=
     if ref_arm.available():
         job = reference_job(workload, raw, pairs)
         res = ref_arm.run(job, procs, seconds)
-        fuzzy = workload["kind"].startswith("fuzzy")
+        fuzzy = workload["kind"] in ("fuzzy", "fuzzyterm", "mesh")
         sample = (f"{res['blocks']} blocks of {job['rows_per_block']} x {len(job['right']['Identifier'])} items of "
                   f"{pairs[0][0]} x {pairs[0][1]} ({res['pairs']} item pairs, {res['evals']:.0f} pair-scores) through the "
                   f"unmodified reference's {job['what']} from oracle/_ref (manifest {ref_arm.manifest_digest()}), "
@@ -485,7 +515,7 @@ def workload_config(name: str, wl: dict, packs, pairs, world: int) -> dict:
 
 
 def dtype_of(wl: dict) -> str:
-    return "int32+f64" if not wl["kind"].startswith("fuzzy") else "u64+f64"
+    return "u64+f64" if wl["kind"] in ("fuzzy", "fuzzyterm", "mesh") else "int32+f64"
 
 
 def run_reference_arm(args, rank: int, world: int):
@@ -535,7 +565,7 @@ class Prepared:
         BUILD_INFO.clear()
         self.packs, self.raw, self.pairs = build_workload(wl, 0)   # the same problem on every rank
         self.host_pack_s = BUILD_INFO.get("host_pack_s", 0.0)
-        self.flat, self.thr = wl["kind"] == "fuzzy", wl["thr"]
+        self.flat, self.thr = wl["kind"] in ("fuzzy", "mesh"), wl["thr"]
         self.config = workload_config(name, wl, self.packs, self.pairs, world)
         counts = [schedule_counts(self.packs[a], self.packs[b]) for a, b in self.pairs]
         self.evals_step = sum(c[0] for c in counts)

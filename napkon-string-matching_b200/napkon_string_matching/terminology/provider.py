@@ -6,8 +6,10 @@ with ``fuzzy_match``, kept at or above a threshold, best synonym per heading id 
 The reference scores one term at a time with ``np.vectorize(fuzzy_match)`` over a deep copy of
 the synonym frame, inside a fork pool (prepare/match_preparator.py:55-67).  Here all terms of a
 cohort are scored against all synonyms in one all-pairs launch of the fuzzy kernel
-(:meth:`TerminologyProvider.get_matches_many`); the per-term post-processing (sort by score,
-``drop_duplicates("Id")``) stays on the host and only sees the kept pairs.
+(:meth:`TerminologyProvider.get_matches_many`): at the configured threshold (config.yml
+``tokens.score_threshold: 0.85``) the kernel's distance bound proves nearly every term x synonym
+pair below the threshold without computing its LCS.  The post-processing (sort by score,
+``drop_duplicates("Id")``) is one vectorised pass over the kept pairs of all terms.
 
 Reading MeSH from Postgres (mesh.py:122-168) is ETL and out of scope: the synonym / heading
 frames are handed in (the reference's own tests inject them the same way, test_mesh.py:19-24).
@@ -78,18 +80,22 @@ class MeshProvider:
         rows = [[default_process(s)] for s in syn_terms]
         pq, ps = pack.pack_strings(queries, rows)
         rec = engine.all_pairs(engine.upload(pq), engine.upload(ps), score_threshold, flat=True)
-        # per term: best score first (ties keep the synonym frame's order), one row per Id
+        # per term: best score first (ties keep the synonym frame's order), one row per Id —
+        # sort_values(Score, descending) + drop_duplicates("Id") of mesh.py:213-218, for all terms at
+        # once: after the sort the FIRST record of every (term, Id) is the one that survives
         order = np.lexsort((rec["right"], -rec["score"], rec["left"]))
         rec = rec[order]
+        gid, _ = pd.factorize(ids)
+        key = rec["left"].astype(np.int64) * (int(gid.max(initial=0)) + 1) + gid[rec["right"]]
+        _, first = np.unique(key, return_index=True)
+        rec = rec[np.sort(first)]
         out: List[List[Match]] = [[] for _ in terms]
         bounds = np.searchsorted(rec["left"], np.arange(len(terms) + 1))
+        r_ids, r_terms, r_scores = ids[rec["right"]], syn_terms[rec["right"]], rec["score"].tolist()
         for t in range(len(terms)):
-            seen = set()
-            for r, score in zip(rec["right"][bounds[t]:bounds[t + 1]], rec["score"][bounds[t]:bounds[t + 1]]):
-                if ids[r] in seen:
-                    continue
-                seen.add(ids[r])
-                out[t].append((ids[r], syn_terms[r], float(score)))
+            lo, hi = int(bounds[t]), int(bounds[t + 1])
+            if hi > lo:
+                out[t] = list(zip(r_ids[lo:hi].tolist(), r_terms[lo:hi].tolist(), r_scores[lo:hi]))
         return out
 
 

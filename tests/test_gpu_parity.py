@@ -383,8 +383,7 @@ def test_pipelined_row_blocks_give_the_same_records(engine):
     pr = pack.pack_suffix_id_sets(lens, flat, 30000)
     dl, dr = engine.upload(pl), engine.upload(pr)
     key = lambda a: a[np.lexsort((a["right"], a["left"]))]
-    old = engine.pipeline_d2h, engine.PIPELINE_BLOCK_BYTES, engine.PIPELINE_MIN_PAIRS
-    engine.PIPELINE_MIN_PAIRS = 1
+    engine.PIPELINE_MIN_PAIRS = 1     # instance overrides of the class constants, dropped below
     try:
         for thr in (0.1, 0.7):
             engine.pipeline_d2h = False
@@ -401,7 +400,9 @@ def test_pipelined_row_blocks_give_the_same_records(engine):
             part = key(engine.all_pairs(dl, dr, thr, rows=(1000, 19000)))
             assert np.array_equal(part, want[(want["left"] >= 1000) & (want["left"] < 19000)])
     finally:
-        engine.pipeline_d2h, engine.PIPELINE_BLOCK_BYTES, engine.PIPELINE_MIN_PAIRS = old
+        engine.pipeline_d2h = True
+        for name in ("PIPELINE_BLOCK_BYTES", "PIPELINE_MIN_PAIRS"):
+            engine.__dict__.pop(name, None)
 
 
 def _keyed(rec, n_right):

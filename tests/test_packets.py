@@ -108,19 +108,17 @@ def test_packets_equal_pairs_and_oracle(engine):
 def test_probe_sized_pipeline_has_no_reruns(engine, monkeypatch):
     """A job large enough for the probe path: the probe block sizes the arenas of the rest (no
     overflow re-run), dense results switch to packets, and the union is the plain result."""
-    from napkon_string_matching.gpu.engine import Engine
-
     pl, pr = _tokenid_packs(9000, 3000)
     dl, dr = engine.upload(pl), engine.upload(pr)
-    monkeypatch.setattr(Engine, "PIPELINE_MIN_PAIRS", 1 << 20)
-    monkeypatch.setattr(Engine, "PIPELINE_BLOCK_BYTES", 4 << 20)   # several blocks
+    monkeypatch.setattr(engine, "PIPELINE_MIN_PAIRS", 1 << 20)
+    monkeypatch.setattr(engine, "PIPELINE_BLOCK_BYTES", 4 << 20)   # several blocks
     old = engine.compact
     try:
         engine.compact = "auto"
         piped = engine.all_pairs(dl, dr, 0.1)
         info = dict(engine.last_info)
         engine.compact = False
-        monkeypatch.setattr(Engine, "PIPELINE_MIN_PAIRS", 1 << 62)
+        monkeypatch.setattr(engine, "PIPELINE_MIN_PAIRS", 1 << 62)
         plain = engine.all_pairs(dl, dr, 0.1)
     finally:
         engine.compact = old
@@ -129,7 +127,7 @@ def test_probe_sized_pipeline_has_no_reruns(engine, monkeypatch):
     assert_same_triples((piped["left"], piped["right"], piped["score"]),
                         (plain["left"], plain["right"], plain["score"]))
     # sparse results stay in the 16-byte format
-    monkeypatch.setattr(Engine, "PIPELINE_MIN_PAIRS", 1 << 20)
+    monkeypatch.setattr(engine, "PIPELINE_MIN_PAIRS", 1 << 20)
     engine.compact = "auto"
     sparse = engine.all_pairs(dl, dr, 0.6)
     assert engine.last_info["packets"] == 0 and engine.last_info["reruns"] == 0
