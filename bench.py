@@ -97,6 +97,11 @@ def build_tokenids(n: int, rank: int):
     packs, raw = {}, {}
     for name, seed in seeds.items():
         lens, flat = syn.token_id_level_sets(n, seed + 1000 * rank)
+        if os.environ.get("NSM_EXP_SORTK"):   # experiment: items ordered by level count
+            order = np.argsort(lens, kind="stable")
+            starts = np.cumsum(lens) - lens
+            idx = np.repeat(starts[order], lens[order]) + (np.arange(int(lens.sum())) - np.repeat(np.cumsum(lens[order]) - lens[order], lens[order]))
+            lens, flat = lens[order], flat[idx]
         raw[name] = (lens, flat)
         t0 = time.perf_counter()
         packs[name] = pack.pack_suffix_id_sets(lens, flat, 30000)

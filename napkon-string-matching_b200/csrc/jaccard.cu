@@ -45,6 +45,21 @@ constexpr int J_OUT = 48;         // staged output records per warp
 constexpr int J_UNROLL = 6;       // steps of stage B, all straight-line code
 constexpr int J_AUNROLL = 4;      // left items per round of stage A
 constexpr int J_QA = 32 + 32 * J_AUNROLL;  // queue A capacity
+static_assert(J_UNIT_LEFT == 512 && JT_THREADS == 128, "queue entries are 9 + 7 bits; the tile table covers 512 rows");
+// Stage A tiles: 32 right columns (a quarter of the block) x a range of left rows.  The warps of a
+// CTA draw tiles from a shared counter; the ranges shrink towards the end of the unit (guided
+// self-scheduling), so that the block barrier at the end waits for a 16-row tile at most.
+constexpr int J_TILE_RANGES = 10;
+__device__ const uint16_t g_tile_begin[J_TILE_RANGES + 1] = {0, 128, 256, 320, 384, 416, 448, 464, 480, 496, 512};
+#ifndef NSM_J_DYN
+#define NSM_J_DYN 1   // 1: the warps of a CTA draw stage A tiles from a shared counter; 0: fixed right quarters
+#endif
+#ifndef NSM_J_COARSE
+#define NSM_J_COARSE 1  // 1: coarse first half of stage B at low thresholds (see SPLIT == 0)
+#endif
+#ifndef NSM_J_CFLAT
+#define NSM_J_CFLAT 1  // 1: branch-free step arithmetic in stage C's fast path
+#endif
 constexpr uint32_t NO_TWO = 0xffffffffu;   // JaccardParams::two_small: the >= 2 bits test is off
 
 struct JaccardParams {
@@ -54,6 +69,7 @@ struct JaccardParams {
     uint32_t any_depth;  // D of stage A; 0: use the packed all-level item_any
     uint32_t bound_split;  // stage B tests the bound after this many steps (1..J_UNROLL)
     uint32_t two_small;    // TWO kernels: a step-1 level of at most this many ids makes its item "wild"
+    uint32_t dyn_tiles;    // 1: the warps of a CTA draw stage A tiles from a shared counter (see g_tile_begin)
     uint32_t n_lchunks, n_rblocks;
 };
 
@@ -68,13 +84,16 @@ struct __align__(16) JaccardSmem {
     uint32_t r_info[J_SLOTS][JT_THREADS];  // size | fold count << 16
     uint32_t r_k[JT_THREADS];
     float rcp_up[J_RCP];
-    uint32_t qa[J_WARPS][J_QA];
-    uint32_t qm[J_WARPS][64];   // survivors of the first D bound steps ...
-    float qm_ub[J_WARPS][64];   // ... and their partial bound
-    uint32_t qb[J_WARPS][64];
+    ulonglong2 r_any[JT_THREADS];          // stage A word of every right column of the block
+    float qm_ub[J_WARPS][64];   // partial bound of the entries of qm
+    // the queues hold unit-local pair positions: left row (9 bits) << 7 | right column (7 bits)
+    uint16_t qa[J_WARPS][J_QA];
+    uint16_t qm[J_WARPS][64];   // survivors of the first half of stage B
+    uint16_t qb[J_WARPS][64];
     uint16_t l_k[J_UNIT_LEFT];
     unsigned long long stats[NSM_N_STATS];
     uint64_t bar;  // mbarrier of the right block's bulk copies
+    uint32_t tile_next;  // next stage A tile of the unit (the warps draw from it)
 };
 
 // len(A & B) / len(A | B) as the correctly rounded float64 quotient of two small integers without
@@ -369,31 +388,26 @@ jaccard_allpairs_kernel(const JaccardParams p) {
             }
         }
         const uint32_t r = r0 + tid;
-        const bool r_valid = r < p.R.n_items;
-        uint32_t kr = 0;
-        uint64_t rany_h = 0, rany_t = 0;
-        if (r_valid) {
-            kr = __ldg(p.R.item_k + r);
-            if (p.any_depth == 0) {
-                const ulonglong2 any = __ldg(reinterpret_cast<const ulonglong2 *>(p.R.item_any) + r);
-                rany_h = any.x; rany_t = any.y;
-            }
-        }
-        s.r_k[tid] = kr;
-        // ---- the unit's left items: stage A word and level count -------------------------
-        for (uint32_t li = tid; li < nl; li += JT_THREADS) {
-            const uint32_t k = __ldg(p.L.item_k + l0 + li);
+        s.r_k[tid] = r < p.R.n_items ? __ldg(p.R.item_k + r) : 0u;
+        if (tid == 0) s.tile_next = 0;
+        // ---- the unit's left items: stage A word and level count (rows beyond nl: a word that
+        // ---- shares no bit with anything, so stage A needs no bounds test) ----------------
+        for (uint32_t li = tid; li < (uint32_t)J_UNIT_LEFT; li += JT_THREADS) {
             ulonglong2 any = make_ulonglong2(0, 0);
-            if (pass_all || k == 0) {
-                any.x = any.y = ~0ull;
-            } else if (p.any_depth == 0) {
-                any = __ldg(reinterpret_cast<const ulonglong2 *>(p.L.item_any) + l0 + li);
-            } else if (TWO) {
-                any = two_word(__ldg(l_slot_ht + l0 + li), __ldg(p.L.slot_info + l0 + li), p.two_small, true);
-            } else {
-                for (uint32_t sl = 0; sl < min(p.any_depth, SL); ++sl) {
-                    const ulonglong2 ht = __ldg(l_slot_ht + (size_t)sl * p.L.slot_stride + l0 + li);
-                    any.x |= ht.x; any.y |= ht.y;
+            uint32_t k = 0;
+            if (li < nl) {
+                k = __ldg(p.L.item_k + l0 + li);
+                if (pass_all || k == 0) {
+                    any.x = any.y = ~0ull;
+                } else if (p.any_depth == 0) {
+                    any = __ldg(reinterpret_cast<const ulonglong2 *>(p.L.item_any) + l0 + li);
+                } else if (TWO) {
+                    any = two_word(__ldg(l_slot_ht + l0 + li), __ldg(p.L.slot_info + l0 + li), p.two_small, true);
+                } else {
+                    for (uint32_t sl = 0; sl < min(p.any_depth, SL); ++sl) {
+                        const ulonglong2 ht = __ldg(l_slot_ht + (size_t)sl * p.L.slot_stride + l0 + li);
+                        any.x |= ht.x; any.y |= ht.y;
+                    }
                 }
             }
             s.l_any[li] = any;
@@ -401,35 +415,61 @@ jaccard_allpairs_kernel(const JaccardParams p) {
         }
         mbar_wait(&s.bar, bar_parity);  // the right block has landed
         bar_parity ^= 1u;
-        if (TWO) {
-            const ulonglong2 w = two_word(s.r_ht[0][tid], s.r_info[0][tid], p.two_small, false);
-            rany_h = w.x; rany_t = w.y;
-        } else {
-            for (uint32_t sl = 0; sl < min(p.any_depth, SR); ++sl) {
-                const ulonglong2 ht = s.r_ht[sl][tid];
-                rany_h |= ht.x; rany_t |= ht.y;
+        {   // stage A word of my right column.  A column beyond the cohort shares no bit with
+            // anything; threshold <= 0 keeps every pair; an item without levels must reach stage C,
+            // which tells "both empty: score 0" from "one empty: IndexError upstream"
+            ulonglong2 any = make_ulonglong2(0, 0);
+            if (r < p.R.n_items) {
+                if (pass_all || s.r_k[tid] == 0) {
+                    any.x = any.y = ~0ull;
+                } else if (TWO) {
+                    any = two_word(s.r_ht[0][tid], s.r_info[0][tid], p.two_small, false);
+                } else if (p.any_depth == 0) {
+                    any = __ldg(reinterpret_cast<const ulonglong2 *>(p.R.item_any) + r);
+                } else {
+                    for (uint32_t sl = 0; sl < min(p.any_depth, SR); ++sl) {
+                        const ulonglong2 ht = s.r_ht[sl][tid];
+                        any.x |= ht.x; any.y |= ht.y;
+                    }
+                }
             }
+            s.r_any[tid] = any;
         }
-        if (!r_valid) rany_h = rany_t = 0;
-        // threshold <= 0 keeps every pair; an item without levels must reach stage C, which
-        // tells "both empty: score 0" from "one empty: IndexError upstream"
-        if (r_valid && (pass_all || kr == 0)) rany_h = rany_t = ~0ull;
         __syncthreads();
 
-        // The funnel as one loop, so that each stage's code exists once: fill queue A from stage
-        // A until it holds a warp's worth (or the unit is exhausted), run stage B on 32 entries,
-        // run stage C whenever queue B holds 32 (or everything before it is done).
-        uint32_t qa_n = 0, qm_n = 0, qb_n = 0, li_next = 0;  // warp-uniform
+        // Stage A runs tile by tile (see g_tile_begin): a warp whose columns hold frequent tokens
+        // (many survivors, long stages B and C) simply draws fewer tiles.
+        const uint32_t n_tiles = 4u * J_TILE_RANGES;
+        uint32_t qa_n = 0, qm_n = 0, qb_n = 0;  // warp-uniform
+        uint32_t li_next = 0, li_end = 0, rc_mine = (warp << 5) | lane;  // the tile the warp is in
+        uint64_t rany_h = 0, rany_t = 0;
+        bool unit_done = false;
+        if (!p.dyn_tiles) {   // fixed quarters: one tile per warp
+            const ulonglong2 w = s.r_any[rc_mine];
+            rany_h = w.x; rany_t = w.y; li_end = (nl + 3u) & ~3u;
+        }
         while (true) {
             // ---- stage A: left items x my right item ----------------------------------------
-            while (qa_n < 32 && li_next < nl) {
+            while (qa_n < 32 && !unit_done) {
+                if (li_next >= li_end) {
+                    if (!p.dyn_tiles) { unit_done = true; break; }
+                    uint32_t tile = 0;
+                    if (lane == 0) tile = atomicAdd(&s.tile_next, 1u);
+                    tile = __shfl_sync(FULL_MASK, tile, 0);
+                    if (tile >= n_tiles) { unit_done = true; break; }
+                    rc_mine = ((tile & 3u) << 5) | lane;
+                    li_next = g_tile_begin[tile >> 2];
+                    li_end = min((uint32_t)g_tile_begin[(tile >> 2) + 1], (nl + 3u) & ~3u);
+                    const ulonglong2 w = s.r_any[rc_mine];
+                    rany_h = w.x; rany_t = w.y;
+                    continue;   // a range beyond the unit's rows is empty
+                }
                 // four left items per round: four independent load -> test -> vote chains
                 bool pass[J_AUNROLL];
                 unsigned m[J_AUNROLL];
 #pragma unroll
                 for (int u = 0; u < J_AUNROLL; ++u) {
-                    const uint32_t li = min(li_next + u, nl - 1);
-                    const ulonglong2 lany = s.l_any[li];
+                    const ulonglong2 lany = s.l_any[li_next + u];
                     if (TWO) {
                         // shared bits of the step-1 levels: at least two, or one next to a wild flag
                         const uint64_t z = lany.x & rany_h, w = lany.y & rany_t;
@@ -437,22 +477,20 @@ jaccard_allpairs_kernel(const JaccardParams p) {
                                        w1 = (uint32_t)(w >> 32), wc = w1 & 0x3fffffffu;
                         const uint32_t zz = z0 | z1, ww = w0 | wc, any1 = zz | ww;
                         const uint32_t multi = (any1 & (any1 - 1u)) | (z0 & z1) | (w0 & wc) | (zz & ww);
-                        pass[u] = r_valid && li_next + u < nl && any1 != 0 && (multi | (w1 >> 30)) != 0;
+                        pass[u] = any1 != 0 && (multi | (w1 >> 30)) != 0;
                     } else {
-                        pass[u] = r_valid && li_next + u < nl &&
-                                  ((lany.x & rany_h) | (lany.y & rany_t)) != 0;
+                        pass[u] = ((lany.x & rany_h) | (lany.y & rany_t)) != 0;
                     }
                     m[u] = __ballot_sync(FULL_MASK, pass[u]);
                 }
 #pragma unroll
                 for (int u = 0; u < J_AUNROLL; ++u) {
                     if (pass[u])
-                        s.qa[warp][qa_n + __popc(m[u] & lanemask_lt())] = ((li_next + u) << 5) | lane;
+                        s.qa[warp][qa_n + __popc(m[u] & lanemask_lt())] = ((li_next + u) << 7) | rc_mine;
                     qa_n += __popc(m[u]);
                 }
                 li_next += J_AUNROLL;
             }
-            const bool unit_done = li_next >= nl;
             if (qa_n == 0 && qm_n == 0 && qb_n == 0 && unit_done) break;
             __syncwarp();
 
@@ -477,7 +515,7 @@ jaccard_allpairs_kernel(const JaccardParams p) {
                 qa_n -= take;
                 const bool active = lane < take;
                 const uint32_t entry = active ? s.qa[warp][qa_n + lane] : 0u;
-                const uint32_t li = entry >> 5, rc = (warp << 5) | (entry & 31u);
+                const uint32_t li = entry >> 7, rc = entry & 127u;
                 const uint32_t kl = s.l_k[li], c_kr = s.r_k[rc];
                 bool pass = active;
                 // the category predicate runs here, once per round of survivors, not per pair of
@@ -489,13 +527,45 @@ jaccard_allpairs_kernel(const JaccardParams p) {
                 if (pass && !pass_all && kl != 0 && c_kr != 0) {
                     const uint32_t kmax = flat ? 1u : max(kl, c_kr);
                     ++st_bound;
+                    if (SPLIT == 0) {
+                        // COARSE first half (low thresholds, D >= 3; nested levels on both sides, every
+                        // level in a slot).  A pair that shares no bit at step 2 has J_1 = J_2 = 0
+                        // (levels are nested: step 1's sets lie inside step 2's).  For its steps
+                        // 3..T (T = J_UNROLL): I_t <= I_T <= ih, the bound from step T's summaries, and
+                        // the unions only grow, U_t >= U_3 >= a_3 + b_3 - min(ih, a_3, b_3) = umin, so
+                        // every J_t <= jc = min(1, ih / umin) and
+                        //   score <= (2^-2 - 2^-min(T, kmax)) jc + [kmax > T] (2^-T - 2^-kmax).
+                        // Pairs that share a bit at step 2, or whose coarse bound reaches the
+                        // threshold, get the per-step bound of all T steps in the second half.
+                        const uint32_t sl2 = min(2u, SL) - 1, sl3 = min(3u, SL) - 1, slT = min((uint32_t)J_UNROLL, SL) - 1;
+                        const uint32_t sr2 = min(2u, SR) - 1, sr3 = min(3u, SR) - 1, srT = min((uint32_t)J_UNROLL, SR) - 1;
+                        const size_t item = (size_t)l0 + li;
+                        const ulonglong2 A2 = __ldg(l_slot_ht + (size_t)sl2 * p.L.slot_stride + item);
+                        const ulonglong2 AT = __ldg(l_slot_ht + (size_t)slT * p.L.slot_stride + item);
+                        const uint32_t iaT = __ldg(p.L.slot_info + (size_t)slT * p.L.slot_stride + item);
+                        const uint32_t ia3 = __ldg(p.L.slot_info + (size_t)sl3 * p.L.slot_stride + item);
+                        const ulonglong2 B2 = s.r_ht[sr2][rc];
+                        const bool share2 = ((A2.x & B2.x) | (A2.y & B2.y)) != 0;
+                        const uint32_t ih = bound_intersection(AT, iaT, s.r_ht[srT][rc], s.r_info[srT][rc], exact_bits);
+                        const uint32_t a3 = ia3 & 0xffffu, b3 = s.r_info[sr3][rc] & 0xffffu;
+                        const uint32_t umin = a3 + b3 - min(ih, min(a3, b3));
+                        // umin == 0: both step-3 sets empty (0 / 0 upstream): let stage C see the pair
+                        const float jc = umin == 0 ? 1.0f
+                            : fminf(1.0f, __fmul_ru((float)ih, s.rcp_up[min(umin, (uint32_t)J_RCP - 1)]));
+                        const uint32_t kt = min(kmax, (uint32_t)J_UNROLL);
+                        const float wsum = kt > 2 ? __fsub_ru(0.25f, pow2_neg(kt)) : 0.0f;
+                        const float grant = kmax > (uint32_t)J_UNROLL
+                            ? __fsub_ru(pow2_neg(J_UNROLL), pow2_neg(kmax)) : 0.0f;
+                        pass = share2 || __fmaf_ru(jc, wsum, grant) >= p.thr_lo;
+                    } else {
 #pragma unroll
-                    for (uint32_t t = 1; t <= (uint32_t)J_UNROLL; ++t)
-                        if (t <= (uint32_t)SPLIT) ub = bound_step(t, li, rc, kmax, ub);
-                    // weights still to come after step D: 2^-D - 2^-kmax
-                    const float rem = kmax > (uint32_t)SPLIT
-                        ? __fsub_ru(pow2_neg(SPLIT), pow2_neg(kmax)) : 0.0f;
-                    pass = __fadd_ru(ub, rem) >= p.thr_lo;
+                        for (uint32_t t = 1; t <= (uint32_t)J_UNROLL; ++t)
+                            if (t <= (uint32_t)SPLIT) ub = bound_step(t, li, rc, kmax, ub);
+                        // weights still to come after step D: 2^-D - 2^-kmax
+                        const float rem = kmax > (uint32_t)SPLIT
+                            ? __fsub_ru(pow2_neg(SPLIT), pow2_neg(kmax)) : 0.0f;
+                        pass = __fadd_ru(ub, rem) >= p.thr_lo;
+                    }
                 }
                 const unsigned m = __ballot_sync(FULL_MASK, pass);
                 if (pass) {
@@ -512,13 +582,13 @@ jaccard_allpairs_kernel(const JaccardParams p) {
                 const bool active = lane < take;
                 const uint32_t entry = active ? s.qm[warp][qm_n + lane] : 0u;
                 float ub = active ? s.qm_ub[warp][qm_n + lane] : 0.0f;
-                const uint32_t li = entry >> 5, rc = (warp << 5) | (entry & 31u);
+                const uint32_t li = entry >> 7, rc = entry & 127u;
                 const uint32_t kl = s.l_k[li], c_kr = s.r_k[rc];
                 bool pass = active;
                 if (active && !pass_all && kl != 0 && c_kr != 0) {
                     const uint32_t kmax = flat ? 1u : max(kl, c_kr);
 #pragma unroll
-                    for (uint32_t t = 2; t <= (uint32_t)J_UNROLL; ++t)
+                    for (uint32_t t = 1; t <= (uint32_t)J_UNROLL; ++t)
                         if (t > (uint32_t)SPLIT) ub = bound_step(t, li, rc, kmax, ub);
                     // steps beyond the unrolled ones are not bounded individually: all their
                     // weight, 2^-UNROLL - 2^-kmax, is granted (pairs this lets through are within
@@ -541,7 +611,7 @@ jaccard_allpairs_kernel(const JaccardParams p) {
                 qb_n -= take;
                 const bool active = lane < take;
                 const uint32_t entry = active ? s.qb[warp][qb_n + lane] : 0u;
-                const uint32_t li = entry >> 5, rc = (warp << 5) | (entry & 31u);
+                const uint32_t li = entry >> 7, rc = entry & 127u;
                 const uint32_t c_l = l0 + li, c_r = r0 + rc;
                 const uint32_t kl = s.l_k[li], c_kr = s.r_k[rc];
                 bool ok = active;
@@ -630,6 +700,24 @@ jaccard_allpairs_kernel(const JaccardParams p) {
                             const uint32_t t = t0 + q;
                             uint32_t it = __popcll(A[q].x & B[q].x);
                             const uint64_t tb = A[q].y & B[q].y;
+#if NSM_J_CFLAT
+                            // no data-dependent branch: a zero intersection adds +0.0 (0 / u = +0.0 and
+                            // score + 0.0 * w == score), a step beyond the pair's schedule adds nothing
+                            if (exact_bits) {
+                                it += __popcll(tb);
+                            } else {   // t is warp-uniform: one shift of the packed per-step counts
+                                const uint32_t cnt = (uint32_t)((t <= 8 ? tail_steps.x >> (8 * (t - 1))
+                                                                        : tail_steps.y >> (8 * ((t - 9) & 7))) & 0xffu);
+                                it += (tb != 0 && t <= 16) ? cnt : 0u;
+                            }
+                            const uint32_t un = (ia[q] & 0xffffu) + (ib[q] & 0xffffu) - it;
+                            const bool on = t <= kmax;
+                            st_evals += on ? 1u : 0u;
+                            w *= 0.5;
+                            const double sc = __fma_rn(div_counts(it, un), w, score);
+                            score = on ? sc : score;
+                            zero_union |= on && un == 0;  // 0 / 0: ZeroDivisionError upstream
+#else
                             if (exact_bits) {
                                 it += __popcll(tb);
                             } else if (tb && t <= 16) {
@@ -643,6 +731,7 @@ jaccard_allpairs_kernel(const JaccardParams p) {
                                 if (it) score = __fma_rn(div_counts(it, un), w, score);
                                 else zero_union |= un == 0;  // 0 / 0: ZeroDivisionError upstream
                             }
+#endif
                         }
                     }
                     if (zero_union) {
@@ -813,6 +902,8 @@ static int launch_jaccard_split(const JaccardParams &p, uint64_t n_units, cudaSt
         case 1: return p.two_small != NO_TWO ? launch_jaccard<DEEP, 1, true>(p, n_units, stream)
                                              : launch_jaccard<DEEP, 1>(p, n_units, stream);
         case 2: return launch_jaccard<DEEP, 2>(p, n_units, stream);
+        case 0: if (!DEEP) return launch_jaccard<false, 0>(p, n_units, stream);  // coarse first half
+                return launch_jaccard<DEEP, J_UNROLL>(p, n_units, stream);
         default: return launch_jaccard<DEEP, J_UNROLL>(p, n_units, stream);
     }
 }
@@ -857,6 +948,7 @@ extern "C" int nsm_jaccard_allpairs(const nsm_sets_t *left, const nsm_sets_t *ri
     p.any_depth = 0;
     p.bound_split = J_UNROLL;
     p.two_small = NO_TWO;
+    p.dyn_tiles = 0;
     if (p.thr_lo > 0.0f && !job->flat) {
         const uint32_t kmax = left->max_levels > right->max_levels ? left->max_levels : right->max_levels;
         const float w_last = kmax < 120 ? ldexpf(1.0f, -(int)kmax) : 0.0f;
@@ -866,6 +958,12 @@ extern "C" int nsm_jaccard_allpairs(const nsm_sets_t *left, const nsm_sets_t *ri
             p.any_depth = d < (uint32_t)J_SLOTS ? d : (uint32_t)J_SLOTS;
         // splitting pays when few pairs survive the first half, i.e. at high thresholds (small D)
         p.bound_split = d <= 2 ? d : (uint32_t)J_UNROLL;
+        // low thresholds (D >= 3) over nested levels that all lie in the slots: a coarse first half
+        // (bound_split 0) proves most pairs that share nothing through step 2 below the threshold
+        // deep funnels (D >= 3): stages B and C dominate and their load differs from warp to warp
+        p.dyn_tiles = (NSM_J_DYN && d >= 3) ? 1u : 0u;
+        if (NSM_J_COARSE && d >= 3 && left->nested && right->nested && !l_deep && !r_deep)
+            p.bound_split = 0;
         // D == 1: score <= J_1 / 2 + (1/2 - 2^-Kmax), so a kept pair has J_1 >= jmin.  With at most
         // ONE shared id J_1 <= 1 / (a + b - 1), which is below jmin once a + b > 1 + 1 / jmin: if
         // both step-1 levels hold more than c = floor(floor(1 + 1/jmin) / 2) ids, a pair needs two

@@ -21,7 +21,7 @@ MARKS = [("warp_intersect_count", "uint32_t warp_intersect_count("),
          ("unit staging (TMA, any words)", "for (uint32_t unit = blockIdx.x"),
          ("stage A any", "// ---- stage A:"), ("stage B bound", "// ---- stage B:"),
          ("stage C exact", "// ---- stage C:"), ("compaction", "// ---- threshold compaction"),
-         ("epilogue", "    flush_out();")]
+         ("epilogue", "    if (!packets && !coded) flush_out();")]
 
 
 def main():

@@ -189,3 +189,53 @@ def test_stage_b_bound_is_an_upper_bound_of_the_exact_score(vocab, max_k, per_pa
     assert np.all(ub >= score - 1e-12), np.argwhere(ub < score - 1e-12)[:3]
     # and it is a useful bound, not a trivial one: it separates most pairs from a threshold of 0.3
     assert (ub < 0.3).mean() > 0.3
+
+
+def coarse_first_half(pl, pr, thr, unroll=6):
+    """Stage B's coarse first half (jaccard.cu, SPLIT == 0) restated in real arithmetic: a pair goes
+    on to the per-step bound when it shares a signature bit at step 2, or when
+    (2^-2 - 2^-min(T, kmax)) * min(1, ih_T / umin) + [kmax > T](2^-T - 2^-kmax) reaches the
+    threshold, ih_T being the intersection bound of step T's summaries and umin = a_3 + b_3 -
+    min(ih_T, a_3, b_3) a lower bound of every union from step 3 on."""
+    nl, nr = pl.n_items, pr.n_items
+    slot = lambda t, s: min(t, s) - 1
+    kmax = np.maximum(pl.item_k[:, None].astype(np.int64), pr.item_k[None, :].astype(np.int64))
+    a2, b2 = pl.slot_ht[slot(2, pl.n_slots), :nl], pr.slot_ht[slot(2, pr.n_slots), :nr]
+    share2 = ((a2[:, None, 0] & b2[None, :, 0]) | (a2[:, None, 1] & b2[None, :, 1])) != 0
+    sl, sr = slot(unroll, pl.n_slots), slot(unroll, pr.n_slots)
+    ha, ta, ia = pl.slot_ht[sl, :nl, 0], pl.slot_ht[sl, :nl, 1], pl.slot_info[sl, :nl].astype(np.int64)
+    hb, tb, ib = pr.slot_ht[sr, :nr, 0], pr.slot_ht[sr, :nr, 1], pr.slot_info[sr, :nr].astype(np.int64)
+    both = ta[:, None] & tb[None, :]
+    fold = np.minimum(ia[:, None] >> 16, ib[None, :] >> 16)
+    extra = np.where(fold == 255, 1 << 16, fold) if not (pl.exact_bits and pr.exact_bits) else 0
+    it = np.where(both != 0, popcount(both) + extra, 0)
+    ih = np.minimum(popcount(ha[:, None] & hb[None, :]) + it, np.minimum(ia & 0xFFFF, 1 << 30)[:, None])
+    ih = np.minimum(ih, (ib & 0xFFFF)[None, :])
+    a3 = (pl.slot_info[slot(3, pl.n_slots), :nl] & 0xFFFF).astype(np.int64)[:, None]
+    b3 = (pr.slot_info[slot(3, pr.n_slots), :nr] & 0xFFFF).astype(np.int64)[None, :]
+    umin = a3 + b3 - np.minimum(ih, np.minimum(a3, b3))
+    jc = np.where(umin == 0, 1.0, np.minimum(1.0, ih / np.maximum(umin, 1)))
+    wsum = np.maximum(0.0, 0.25 - 2.0 ** -np.minimum(unroll, kmax).astype(float))
+    grant = np.where(kmax > unroll, 2.0 ** -unroll - 2.0 ** -kmax.astype(float), 0.0)
+    return share2 | (jc * wsum + grant >= float(filter_threshold(thr)))
+
+
+@pytest.mark.parametrize("vocab,max_k,per_part,zipf", [(70, 4, 5, 1.2), (400, 5, 9, 1.2), (3000, 9, 3, 1.3),
+                                                        (20000, 8, 2, 1.1), (500, 9, 2, 1.3), (150, 10, 1, 1.05)])
+def test_coarse_first_half_never_prunes_a_pair_that_reaches_the_threshold(vocab, max_k, per_part, zipf):
+    rng = np.random.default_rng(11 * vocab + max_k)
+    pl, pr = pack.pack_sets(suffix_items(rng, 240, max_k, per_part, vocab, zipf),
+                            suffix_items(rng, 280, max_k, per_part, vocab, zipf))
+    assert pl.nested and pr.nested
+    assert max(pl.max_levels, pr.max_levels) <= min(pl.n_slots, pr.n_slots) + 1   # the kernel's precondition
+    everything, _ = c_oracle.all_pairs(pl, pr, 0.0)
+    score = np.zeros((pl.n_items, pr.n_items))
+    score[everything["left"], everything["right"]] = everything["score"]
+    pruned_some = False
+    for thr in (0.01, 0.03, 0.0625, 0.1, 0.12, 0.2, 0.24):
+        depth, _ = stage_a_parameters(pl, pr, thr)
+        passes = coarse_first_half(pl, pr, thr)
+        reaches = score >= thr
+        assert not np.any(reaches & ~passes), (thr, np.argwhere(reaches & ~passes)[:3])
+        pruned_some |= bool(np.any(~passes & (score > 0)))
+    assert pruned_some     # and it does prune pairs with a non-zero score
