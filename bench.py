@@ -89,6 +89,27 @@ BUILD_INFO: dict = {}   # host_pack_s: seconds the numpy packer took for the wor
 REF_POOL = 4000         # items per side the CPU reference arm may draw its sample from
 
 
+def level_ordered(lens: np.ndarray, flat: np.ndarray):
+    """A token-set cohort in the storage order the product path gives it (gpu/pairing.py:upload_levels,
+    pack.chunked_level_order): items of one level count next to each other in chunks of the kernel's
+    unit, the chunks interleaved.  ``lens``: ids per item (n,) or per part (n, Q); an item's level
+    count is its number of non-empty parts.  NSM_BENCH_ITEM_ORDER=drawn keeps the drawn order."""
+    if os.environ.get("NSM_BENCH_ITEM_ORDER") == "drawn":
+        return lens, flat
+    from napkon_string_matching.gpu import pack
+
+    per_item = lens if lens.ndim == 1 else lens.sum(axis=1)
+    k = lens if lens.ndim == 1 else (lens > 0).sum(axis=1)
+    perm = pack.chunked_level_order(k, 512)
+    if os.environ.get("NSM_BENCH_ITEM_ORDER") == "sorted":   # experiment: no interleaving of the chunks
+        perm = np.argsort(k, kind="stable")
+    start = np.cumsum(per_item) - per_item
+    size = per_item[perm]
+    new_start = np.cumsum(size) - size
+    idx = np.repeat(start[perm] - new_start, size) + np.arange(int(size.sum()), dtype=np.int64)
+    return lens[perm], flat[idx]
+
+
 def build_tokenids(n: int, rank: int):
     from napkon_string_matching import synthetic as syn
     from napkon_string_matching.gpu import pack
@@ -96,12 +117,7 @@ def build_tokenids(n: int, rank: int):
     seeds = {"hap": syn.SEED_LEFT, "pop": syn.SEED_RIGHT, "suep": syn.SEED_THIRD}
     packs, raw = {}, {}
     for name, seed in seeds.items():
-        lens, flat = syn.token_id_level_sets(n, seed + 1000 * rank)
-        if os.environ.get("NSM_EXP_SORTK"):   # experiment: items ordered by level count
-            order = np.argsort(lens, kind="stable")
-            starts = np.cumsum(lens) - lens
-            idx = np.repeat(starts[order], lens[order]) + (np.arange(int(lens.sum())) - np.repeat(np.cumsum(lens[order]) - lens[order], lens[order]))
-            lens, flat = lens[order], flat[idx]
+        lens, flat = level_ordered(*syn.token_id_level_sets(n, seed + 1000 * rank))
         raw[name] = (lens, flat)
         t0 = time.perf_counter()
         packs[name] = pack.pack_suffix_id_sets(lens, flat, 30000)
@@ -114,11 +130,11 @@ def build_term(wl: dict, rank: int):
     from napkon_string_matching import synthetic as syn
     from napkon_string_matching.gpu import pack
 
-    raw = {"left": syn.term_level_sets(wl["n"], syn.SEED_LEFT + 1000 * rank)}
+    raw = {"left": level_ordered(*syn.term_level_sets(wl["n"], syn.SEED_LEFT + 1000 * rank))}
     if wl.get("defs"):
-        raw["right"] = syn.definition_level_sets(wl["n_right"], syn.SEED_DEFS + 1000 * rank)
+        raw["right"] = level_ordered(*syn.definition_level_sets(wl["n_right"], syn.SEED_DEFS + 1000 * rank))
     else:
-        raw["right"] = syn.term_level_sets(wl["n_right"], syn.SEED_RIGHT + 1000 * rank)
+        raw["right"] = level_ordered(*syn.term_level_sets(wl["n_right"], syn.SEED_RIGHT + 1000 * rank))
     t0 = time.perf_counter()
     rank_map = pack.frequency_rank([f for _, f in raw.values()], 20000)
     packs = {k: pack.pack_part_id_sets(pl, f, 20000, rank_map) for k, (pl, f) in raw.items()}

@@ -256,6 +256,44 @@ int nsm_pack_sets_measure(const nsm_raw_sets_t *raw, uint32_t *item_tok_off, uin
 int nsm_pack_sets_fill(const nsm_raw_sets_t *raw, const uint32_t *item_tok_off, const nsm_sets_t *out,
                        uint32_t *flags, void *stream);
 
+/* ---- device-side string packing (second half) -------------------------------
+ * Applies the default processor of fuzz.QRatio (score_functions.py:27; rapidfuzz 2.1.x
+ * utils.default_process: every non-alphanumeric code point becomes a blank, the ends are trimmed,
+ * the rest is lower-cased) to the level strings join_sorted produced (score_functions.py:16-17)
+ * and writes the `chr` and `level_hist` arrays of nsm_strings_t, bit-identical to the host packer
+ * (napkon_string_matching/gpu/pack.py:pack_strings).  The host keeps what is per distinct code
+ * point (its processed form, Python's Unicode tables) and per level (ordering, offsets); the GPU
+ * does what is per character. */
+#define NSM_STR_SYM_NONE 0xffffu /* cp_sym entry of a code point the host did not map */
+#define NSM_STR_FLAG_UNMAPPED 1u /* a code point >= table_len or mapped to NSM_STR_SYM_NONE */
+
+typedef struct nsm_raw_strings {
+    const uint32_t *level_off; /* [n_levels + 1] start of level g's code points in cps */
+    const uint32_t *cps;       /* [n_cps] UTF-32 code points of the unprocessed level strings */
+    const uint16_t *cp_sym;    /* [table_len] code point -> symbol (index of its processed form) */
+    uint32_t n_levels;
+    uint32_t n_cps;
+    uint32_t table_len;
+    uint32_t blank_sym; /* the symbol of ' ': what the trim removes */
+} nsm_raw_strings_t;
+
+/* Pass 1: first[g] = index of level g's first character that survives the trim, len[g] = length of
+ * the processed string (0 when nothing survives); both device uint32[n_levels].  flags: device
+ * uint32, OR of NSM_STR_FLAG_*. */
+int nsm_pack_strings_measure(const nsm_raw_strings_t *raw, uint32_t *first, uint32_t *len,
+                             uint32_t *flags, void *stream);
+
+/* Pass 2: for every STORED level s (the host ordered the items by the length of their longest
+ * level, pack.py:pack_strings): the codes sym_code[cp_sym[c]] of the characters
+ * first[src_level[s]] .. + level_len[s] of raw level src_level[s] go to chr + level_chr_off[s],
+ * zero-padded to a multiple of 8 bytes, and their 32 saturating byte counters to
+ * level_hist[s][8].  src_level, level_chr_off, level_len: device uint32[n_stored];
+ * sym_code: device uint8[n_sym]. */
+int nsm_pack_strings_fill(const nsm_raw_strings_t *raw, const uint32_t *first, const uint32_t *src_level,
+                          const uint32_t *level_chr_off, const uint32_t *level_len,
+                          const uint8_t *sym_code, uint32_t n_stored, uint8_t *chr,
+                          uint32_t *level_hist, void *stream);
+
 /* Integer-pipe micro-benchmarks used as roofline denominators: every thread of
  * a blocks x threads grid runs `iters` rounds of 8 independent chains x 4 dependent ops of
  * `kind` (0: LOP3, 1: IADD3, 2: POPC, 3: 64-bit add/sub/and/or LCS step).  *ops_per_thread

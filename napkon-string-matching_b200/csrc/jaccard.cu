@@ -31,6 +31,8 @@
 //              and its accumulation order; score >= threshold in float64.
 // Kept pairs go to a per-warp staging buffer and are flushed with one global atomic per ~50
 // records as coalesced 16-byte stores.
+#include <atomic>
+
 #include "nsm_common.cuh"
 
 namespace nsm {
@@ -54,6 +56,9 @@ __device__ const uint16_t g_tile_begin[J_TILE_RANGES + 1] = {0, 128, 256, 320, 3
 #ifndef NSM_J_DYN
 #define NSM_J_DYN 1   // 1: the warps of a CTA draw stage A tiles from a shared counter; 0: fixed right quarters
 #endif
+#ifndef NSM_J_DYN_UNITS
+#define NSM_J_DYN_UNITS 1  // 1: the CTAs draw their units from a device counter; 0: fixed stride
+#endif
 #ifndef NSM_J_COARSE
 #define NSM_J_COARSE 1  // 1: coarse first half of stage B at low thresholds (see SPLIT == 0)
 #endif
@@ -69,6 +74,7 @@ struct JaccardParams {
     uint32_t any_depth;  // D of stage A; 0: use the packed all-level item_any
     uint32_t bound_split;  // stage B tests the bound after this many steps (1..J_UNROLL)
     uint32_t two_small;    // TWO kernels: a step-1 level of at most this many ids makes its item "wild"
+    uint32_t *unit_counter;  // device counter the CTAs draw their units from (zeroed before the launch)
     uint32_t dyn_tiles;    // 1: the warps of a CTA draw stage A tiles from a shared counter (see g_tile_begin)
     uint32_t n_lchunks, n_rblocks;
 };
@@ -94,6 +100,7 @@ struct __align__(16) JaccardSmem {
     unsigned long long stats[NSM_N_STATS];
     uint64_t bar;  // mbarrier of the right block's bulk copies
     uint32_t tile_next;  // next stage A tile of the unit (the warps draw from it)
+    uint32_t next_unit;  // the unit this CTA runs after the current one
 };
 
 // len(A & B) / len(A | B) as the correctly rounded float64 quotient of two small integers without
@@ -367,8 +374,13 @@ jaccard_allpairs_kernel(const JaccardParams p) {
         return s.r_ht[sr][rc];
     };
 
+    // Units are handed out through a device counter: a CTA takes its next unit when it is done with
+    // the current one (the first one is its block index), so no CTA's share depends on how the cost
+    // of the units varies with their position.  Thread 0 draws the next unit while the current one
+    // is staged; everybody picks it up behind the staging barrier.
     const uint32_t n_units = p.n_lchunks * p.n_rblocks;
-    for (uint32_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    uint32_t unit = blockIdx.x;
+    while (unit < n_units) {
         const uint32_t rb = unit / p.n_lchunks, lchunk = unit - rb * p.n_lchunks;
         const uint32_t r0 = rb * JT_THREADS;
         const uint32_t l0 = p.job.l_row_begin + lchunk * J_UNIT_LEFT;
@@ -389,7 +401,10 @@ jaccard_allpairs_kernel(const JaccardParams p) {
         }
         const uint32_t r = r0 + tid;
         s.r_k[tid] = r < p.R.n_items ? __ldg(p.R.item_k + r) : 0u;
-        if (tid == 0) s.tile_next = 0;
+        if (tid == 0) {
+            s.tile_next = 0;
+            s.next_unit = p.unit_counter ? gridDim.x + atomicAdd(p.unit_counter, 1u) : unit + gridDim.x;
+        }
         // ---- the unit's left items: stage A word and level count (rows beyond nl: a word that
         // ---- shares no bit with anything, so stage A needs no bounds test) ----------------
         for (uint32_t li = tid; li < (uint32_t)J_UNIT_LEFT; li += JT_THREADS) {
@@ -436,6 +451,7 @@ jaccard_allpairs_kernel(const JaccardParams p) {
             s.r_any[tid] = any;
         }
         __syncthreads();
+        const uint32_t unit_after = s.next_unit;
 
         // Stage A runs tile by tile (see g_tile_begin): a warp whose columns hold frequent tokens
         // (many survivors, long stages B and C) simply draws fewer tiles.
@@ -868,6 +884,7 @@ jaccard_allpairs_kernel(const JaccardParams p) {
             if (coded) flush_cpacket(out_n, l0, r0); else flush_packet(out_n, l0, r0);
             out_n = 0;
         }
+        unit = unit_after;
     }
     if (!packets && !coded) flush_out();
 
@@ -883,8 +900,28 @@ jaccard_allpairs_kernel(const JaccardParams p) {
     }
 }
 
+// Unit counters: a small per-device pool, one entry per launch in flight (round robin), zeroed on
+// the launch's stream right before it.
+constexpr int J_COUNTERS = 256;
+__device__ uint32_t g_unit_counters[J_COUNTERS];
+
+static uint32_t *next_unit_counter(cudaStream_t stream) {
+    static std::atomic<uint32_t> ticket{0};
+    uint32_t *base = nullptr;
+    if (cudaGetSymbolAddress(reinterpret_cast<void **>(&base), g_unit_counters) != cudaSuccess) return nullptr;
+    uint32_t *ctr = base + ticket.fetch_add(1) % J_COUNTERS;
+    if (cudaMemsetAsync(ctr, 0, sizeof(uint32_t), stream) != cudaSuccess) return nullptr;
+    return ctr;
+}
+
 template <bool DEEP, int SPLIT, bool TWO = false>
-static int launch_jaccard(const JaccardParams &p, uint64_t n_units, cudaStream_t stream) {
+static int launch_jaccard(const JaccardParams &p_in, uint64_t n_units, cudaStream_t stream) {
+    JaccardParams p = p_in;
+    p.unit_counter = NSM_J_DYN_UNITS ? next_unit_counter(stream) : nullptr;
+    if (NSM_J_DYN_UNITS && !p.unit_counter) {
+        set_error("unit counter: %s", cudaGetErrorString(cudaGetLastError()));
+        return NSM_ERR_CUDA;
+    }
     const size_t smem = sizeof(JaccardSmem);
     NSM_CUDA_CHECK(cudaFuncSetAttribute(jaccard_allpairs_kernel<DEEP, SPLIT, TWO>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -115,6 +115,7 @@ class Engine:
         self.last_infos: List[Dict] = []
         self.last_info: Dict = {}
         self._packer = None
+        self._string_packer = None
         self.trace: Optional[List[Tuple[float, str]]] = None   # set to [] to collect (host time, label)
 
     @property
@@ -125,6 +126,15 @@ class Engine:
 
             self._packer = DevicePacker(self)
         return self._packer
+
+    @property
+    def string_packer(self):
+        """Device-side string packing (gpu/device_pack.py:DeviceStringPacker) on this engine's device."""
+        if self._string_packer is None:
+            from napkon_string_matching.gpu.device_pack import DeviceStringPacker
+
+            self._string_packer = DeviceStringPacker(self)
+        return self._string_packer
 
     # ------------------------------------------------------------------ uploads
     def _to_device(self, arr) -> torch.Tensor:

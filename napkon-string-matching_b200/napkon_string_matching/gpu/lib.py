@@ -68,7 +68,9 @@ PACK_FLAG_TOO_LARGE, PACK_FLAG_NOT_NESTED, PACK_FLAG_BAD_ID = 1, 2, 4
 
 EXPORTS = ("nsm_version", "nsm_last_error", "nsm_last_launch_count", "nsm_jaccard_allpairs",
            "nsm_qratio_allpairs", "nsm_microbench", "nsm_pack_count_ids", "nsm_pack_scratch_bytes",
-           "nsm_pack_sets_measure", "nsm_pack_sets_fill", "nsm_dict_reset", "nsm_publish")
+           "nsm_pack_sets_measure", "nsm_pack_sets_fill", "nsm_dict_reset", "nsm_publish",
+           "nsm_pack_strings_measure", "nsm_pack_strings_fill")
+STR_SYM_NONE, STR_FLAG_UNMAPPED = 0xffff, 1
 
 
 class NsmSets(C.Structure):
@@ -94,6 +96,12 @@ class NsmRawSets(C.Structure):
                 ("rank", C.c_void_p), ("n_items", C.c_uint32), ("n_groups", C.c_uint32),
                 ("n_ids", C.c_uint32), ("n_vocab", C.c_uint32), ("mode", C.c_uint32),
                 ("reserved_", C.c_uint32)]
+
+
+class NsmRawStrings(C.Structure):
+    _fields_ = [("level_off", C.c_void_p), ("cps", C.c_void_p), ("cp_sym", C.c_void_p),
+                ("n_levels", C.c_uint32), ("n_cps", C.c_uint32), ("table_len", C.c_uint32),
+                ("blank_sym", C.c_uint32)]
 
 
 class NsmJob(C.Structure):
@@ -147,6 +155,13 @@ def load() -> C.CDLL:
     lib.nsm_pack_sets_fill.restype = C.c_int
     lib.nsm_pack_sets_fill.argtypes = [C.POINTER(NsmRawSets), C.c_void_p, C.POINTER(NsmSets),
                                        C.c_void_p, C.c_void_p]
+    lib.nsm_pack_strings_measure.restype = C.c_int
+    lib.nsm_pack_strings_measure.argtypes = [C.POINTER(NsmRawStrings), C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p]
+    lib.nsm_pack_strings_fill.restype = C.c_int
+    lib.nsm_pack_strings_fill.argtypes = [C.POINTER(NsmRawStrings), C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                                          C.c_void_p]
     _lib = lib
     return lib
 

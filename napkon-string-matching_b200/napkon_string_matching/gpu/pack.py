@@ -326,6 +326,31 @@ def _entry_levels(item_level_off, level_tok_off, tok, k) -> Tuple[np.ndarray, bo
     return np.minimum(entry, 255).astype(np.uint8), nested
 
 
+def chunked_level_order(k: np.ndarray, chunk: int) -> np.ndarray:
+    """Storage order for the items of a token-set cohort: ``perm[stored position] = item index``.
+
+    Items are sorted by their level count K and cut into chunks of ``chunk`` items (the kernel's
+    unit: 512 left rows, 128 right columns), so that the items a warp scores together walk
+    ``compare_terms``' schedule for the same number of steps (stage C runs its step loop to the
+    deepest schedule of the 32 pairs of a round; in a mixed cohort a third of those lane-steps are
+    idle).  The chunks are then laid out in bit-reversed order, so that every contiguous row range
+    — a rank's row block, the engine's probe block — holds the cohort's mix of level counts.  A
+    trailing partial chunk stays last (the chunks before it stay aligned)."""
+    k = np.asarray(k, dtype=np.int64)
+    order = np.argsort(k, kind="stable")
+    full = len(k) // chunk
+    if full < 2:
+        return order
+    bits = (full - 1).bit_length()
+    idx = np.arange(1 << bits, dtype=np.int64)
+    rev = np.zeros_like(idx)
+    for b in range(bits):
+        rev |= ((idx >> b) & 1) << (bits - 1 - b)
+    seq = rev[rev < full]
+    head = order[: full * chunk].reshape(full, chunk)[seq].reshape(-1)
+    return np.concatenate([head, order[full * chunk:]])
+
+
 def rank_by_frequency(codes_per_side: List[np.ndarray], n_vocab: int) -> List[np.ndarray]:
     """Renumbers ids so that id 0 is the most frequent token over all sides."""
     if n_vocab == 0:

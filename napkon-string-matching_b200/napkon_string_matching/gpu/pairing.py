@@ -145,8 +145,9 @@ def upload_levels(engine, left_levels, right_levels, score_func: str):
 
     Token sets: the host maps token strings to codes (exact string identity, Q3) and the GPU
     builds the packed arrays (gpu/device_pack.py).  An item beyond the device packer's per-item
-    limit sends the comparison through the numpy packer instead.  Strings are packed on the host
-    (their per-level ``default_process`` is Python string work)."""
+    limit sends the comparison through the numpy packer instead.  Strings: the host joins each
+    level's tokens (``join_sorted``), the GPU applies ``default_process`` and builds the packed
+    arrays (csrc/pack_strings.cu)."""
     from napkon_string_matching.gpu.stages import stage
 
     packer = getattr(engine, "device_packer", None) if KINDS[score_func] == "sets" else None
@@ -162,12 +163,29 @@ def upload_levels(engine, left_levels, right_levels, score_func: str):
                 raws.append(RawSets(item_level_off.astype(np.uint32), level_off.astype(np.uint32),
                                     codes[pos:pos + len(flat)].astype(np.uint32), nsmlib.RAW_LEVELS))
                 pos += len(flat)
+            # items of one level count next to each other, in chunks of the kernel's unit
+            (raws[0], lperm), (raws[1], rperm) = (raws[0].ordered_by_levels(nsmlib.UNIT_LEFT),
+                                                  raws[1].ordered_by_levels(nsmlib.UNIT_RIGHT))
         try:
             with stage("H2D + device packing"):
                 dl, dr = packer.pack(raws, len(uniques), rank="frequency")
-            return dl, dr, (None, None)
+            dl.perm, dr.perm = lperm, rperm
+            return dl, dr, (lperm, rperm)
         except pack.PackTooLarge:
             pass   # the numpy packer below has no per-item limit
+    if KINDS[score_func] == "strings" and getattr(engine, "string_packer", None) is not None:
+        from napkon_string_matching.gpu.device_pack import PackUnsupported
+        from napkon_string_matching.text.process import join_sorted
+
+        with stage("level strings (join_sorted)"):
+            raw = [[[join_sorted(level) if isinstance(level, list) else level for level in lv] for lv in side]
+                   for side in (left_levels, right_levels)]
+        try:
+            with stage("H2D + device packing"):
+                dl, dr = engine.string_packer.pack(raw)
+            return dl, dr, (dl.perm, dr.perm)
+        except PackUnsupported:
+            pass   # a code point whose lower-case form depends on its neighbours: host packer
     with stage("host packing (numpy)"):
         pl, pr = pack_levels(left_levels, right_levels, score_func)
     with stage("H2D"):

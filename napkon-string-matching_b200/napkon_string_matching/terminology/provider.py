@@ -76,10 +76,18 @@ class MeshProvider:
             return [[] for _ in terms]
         engine = default_engine()
         # " ".join(term) is what the reference scores (a str term is joined per character)
-        queries = [[default_process(" ".join(t))] for t in terms]
-        rows = [[default_process(s)] for s in syn_terms]
-        pq, ps = pack.pack_strings(queries, rows)
-        rec = engine.all_pairs(engine.upload(pq), engine.upload(ps), score_threshold, flat=True)
+        from napkon_string_matching.gpu.device_pack import PackUnsupported
+
+        packer = getattr(engine, "string_packer", None)
+        try:   # default_process and the packed arrays on the GPU (csrc/pack_strings.cu)
+            if packer is None:
+                raise PackUnsupported("no device string packer")
+            dq, ds = packer.pack([[[" ".join(t)] for t in terms], [[s] for s in syn_terms]])
+        except PackUnsupported:
+            pq, ps = pack.pack_strings([[default_process(" ".join(t))] for t in terms],
+                                       [[default_process(s)] for s in syn_terms])
+            dq, ds = engine.upload(pq), engine.upload(ps)
+        rec = engine.all_pairs(dq, ds, score_threshold, flat=True)
         # per term: best score first (ties keep the synonym frame's order), one row per Id —
         # sort_values(Score, descending) + drop_duplicates("Id") of mesh.py:213-218, for all terms at
         # once: after the sort the FIRST record of every (term, Id) is the one that survives
