@@ -641,6 +641,8 @@ class Prepared:
         if self.eng.trace is not None:
             self.eng._mark("inputs uploaded / packed (launched)")
         outs, counts = distributed.sharded_run_jobs(self.eng, self.jobs(d), to_host=True, decode=False)
+        if self.eng.trace is not None:
+            self.eng._mark("counts gathered")
         self.last_records = outs
         infos = self.eng.last_infos
         return counts, sum(i["d2h_bytes"] for i in infos), sum(i["packets"] for i in infos), \
@@ -677,7 +679,8 @@ def measure(prep: Prepared, steps: int, warmup: int, rank: int, world: int, int_
             b.record(stream)
             evs.append((a, b))
         torch.cuda.synchronize()
-        return sum(a.elapsed_time(b) for a, b in evs), last
+        timed.steps_ms = [round(a.elapsed_time(b), 3) for a, b in evs]
+        return sum(timed.steps_ms), last
 
     def max_over_ranks(*vals):
         t = torch.tensor(vals, dtype=torch.float64, device="cuda")
@@ -728,8 +731,17 @@ def measure(prep: Prepared, steps: int, warmup: int, rank: int, world: int, int_
     launches0 = eng.launches
     eng.time_kernels, eng.kernel_ms, eng.kernel_launches_timed = True, 0.0, 0
     t0 = time.time()
+    eng.trace = [(time.perf_counter(), "timed region begins")] if os.environ.get("NSM_BENCH_TRACE_TIMED") else None
+    import gc
+
+    gc.collect()
+    gc.disable()   # no collector pause inside a timed step (seen as one 300 ms step in eight at N = 8)
     ms_e2e, (counts_e2e, d2h, packets, reruns, uncoded) = timed(prep.step_e2e, not self_flushing)
     barrier()
+    gc.enable()
+    timed_trace = None
+    if eng.trace:
+        timed_trace = [(round((t - eng.trace[0][0]) * 1e3, 2), label) for t, label in eng.trace][:40]
     t1 = time.time()
     eng.time_kernels = False
     e2e_kernel_ms, e2e_kernel_launches, e2e_launches = eng.kernel_ms, eng.kernel_launches_timed, eng.launches - launches0
@@ -750,6 +762,10 @@ def measure(prep: Prepared, steps: int, warmup: int, rank: int, world: int, int_
     else:
         assert counts_e2e == counts, (counts_e2e, counts)
 
+    e2e_steps_mine = list(timed.steps_ms)
+    per_rank = [0.0] * world
+    per_rank[rank] = ms_e2e / steps
+    e2e_ms_per_rank = [round(v, 3) for v in sum_over_ranks(*per_rank)]
     ms, ms_e2e = max_over_ranks(ms, ms_e2e)
     names = list(stats)
     sums = sum_over_ranks(kernel_ms, launches, kernel_launches, d2h, packets, reruns, uncoded,
@@ -800,6 +816,8 @@ def measure(prep: Prepared, steps: int, warmup: int, rank: int, world: int, int_
                                  "nsm_pair_t: 16 bytes per kept pair",
                 "kernel_ms_per_step": e2e_kernel_ms / steps, "overflow_reruns_per_step": reruns_sum / steps,
                 "collective": "NCCL all-gather of the kept-pair counts, every step" if world > 1 else None,
+                "ms_per_step_by_rank": e2e_ms_per_rank, "ms_steps_rank0": e2e_steps_mine,
+                **({"timed_trace_rank0": timed_trace} if timed_trace else {}),
                 "timeline_ms_rank0": timeline},
         "pack": prep.pack_info,
         "gpu_launches": int(launches_sum),

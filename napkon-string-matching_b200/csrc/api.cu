@@ -1,4 +1,5 @@
 // Entry points that are not kernels: version, error text, job validation, device facts.
+#include <atomic>
 #include <math.h>
 #include <stdarg.h>
 #include <string.h>
@@ -80,6 +81,20 @@ int prepare_job(const nsm_job_t *job, uint32_t n_left, cudaStream_t stream) {
     if (job->out_mode == NSM_OUT_CODED)
         NSM_CUDA_CHECK(cudaMemsetAsync(job->out_exc_count, 0, sizeof(uint64_t), stream));
     return NSM_OK;
+}
+
+// Unit counters: a small per-device pool, one entry per launch in flight (round robin), zeroed on
+// the launch's stream right before it.  Persistent kernels draw their work units from them.
+constexpr int N_UNIT_COUNTERS = 256;
+__device__ uint32_t g_unit_counters[N_UNIT_COUNTERS];
+
+uint32_t *next_unit_counter(cudaStream_t stream) {
+    static std::atomic<uint32_t> ticket{0};
+    uint32_t *base = nullptr;
+    if (cudaGetSymbolAddress(reinterpret_cast<void **>(&base), g_unit_counters) != cudaSuccess) return nullptr;
+    uint32_t *ctr = base + ticket.fetch_add(1) % N_UNIT_COUNTERS;
+    if (cudaMemsetAsync(ctr, 0, sizeof(uint32_t), stream) != cudaSuccess) return nullptr;
+    return ctr;
 }
 
 }  // namespace nsm

@@ -31,8 +31,6 @@
 //              and its accumulation order; score >= threshold in float64.
 // Kept pairs go to a per-warp staging buffer and are flushed with one global atomic per ~50
 // records as coalesced 16-byte stores.
-#include <atomic>
-
 #include "nsm_common.cuh"
 
 namespace nsm {
@@ -898,20 +896,6 @@ jaccard_allpairs_kernel(const JaccardParams p) {
         if (tid < NSM_N_STATS && s.stats[tid])
             atomicAdd(reinterpret_cast<unsigned long long *>(p.job.out_stats) + tid, s.stats[tid]);
     }
-}
-
-// Unit counters: a small per-device pool, one entry per launch in flight (round robin), zeroed on
-// the launch's stream right before it.
-constexpr int J_COUNTERS = 256;
-__device__ uint32_t g_unit_counters[J_COUNTERS];
-
-static uint32_t *next_unit_counter(cudaStream_t stream) {
-    static std::atomic<uint32_t> ticket{0};
-    uint32_t *base = nullptr;
-    if (cudaGetSymbolAddress(reinterpret_cast<void **>(&base), g_unit_counters) != cudaSuccess) return nullptr;
-    uint32_t *ctr = base + ticket.fetch_add(1) % J_COUNTERS;
-    if (cudaMemsetAsync(ctr, 0, sizeof(uint32_t), stream) != cudaSuccess) return nullptr;
-    return ctr;
 }
 
 template <bool DEEP, int SPLIT, bool TWO = false>

@@ -123,4 +123,8 @@ float filter_threshold(double threshold);
 
 int sm_count();
 
+// A zeroed device counter for the launch about to be queued on `stream` (see api.cu); nullptr on a
+// CUDA error.
+uint32_t *next_unit_counter(cudaStream_t stream);
+
 }  // namespace nsm

@@ -44,6 +44,7 @@ struct QflatParams {
     uint32_t r_begin, r_end;
     uint32_t table_len; // entries of the dmax table: max length sum + 1
     uint32_t swap_out;  // 1: emit (right, left): the caller swapped the sides (LCS is symmetric)
+    uint32_t *unit_counter;  // device counter the CTAs draw their units from; NULL: fixed stride
     double thr_eff;     // threshold on QRatio/100 itself (2 x threshold for compare_terms on K = 1)
 };
 
@@ -143,15 +144,21 @@ qratio_flat_kernel(const QflatParams p) {
         for (int x = 0; x < W; ++x) S[x] = sum[x] | (S[x] & ~M[x]);
     };
 
+    // Units are drawn from a device counter (a CTA takes the next one when it is done), and in
+    // falling order of cost: both sides are stored by rising length, so the units with the longest
+    // patterns and texts come first and the kernel ends on the cheap ones.
     const uint32_t n_units = p.n_lgroups * p.n_rblocks;
-    for (uint32_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-        const uint32_t rb = unit / p.n_lgroups, lgroup = unit - rb * p.n_lgroups;
+    uint32_t unit = blockIdx.x;
+    while (unit < n_units) {
+        const uint32_t unit_rev = n_units - 1u - unit;
+        const uint32_t rb = unit_rev / p.n_lgroups, lgroup = unit_rev - rb * p.n_lgroups;
         const uint32_t r = p.r_begin + rb * nthr + tid;
         const bool r_valid = r < p.r_end;
         uint32_t kr = 0, m = 0;
         uint32_t hr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         uint64_t rcat = 0;
         __syncthreads();  // nobody still reads masks or the table of the previous unit / the prologue
+        if (tid == 0) s_misc[1] = p.unit_counter ? gridDim.x + atomicAdd(p.unit_counter, 1u) : unit + gridDim.x;
         if (r_valid) {
             const uint32_t rg0 = __ldg(p.R.item_level_off + r);
             kr = __ldg(p.R.item_level_off + r + 1) - rg0;
@@ -330,6 +337,7 @@ qratio_flat_kernel(const QflatParams p) {
                 b0 += bn;
             }
         }
+        unit = s_misc[1];   // written before the barriers of the tile loop; rewritten behind the next one
     }
     if (p.job.out_stats) {
         for (int o = 16; o; o >>= 1) {
@@ -401,6 +409,11 @@ int qratio_flat_launch(const nsm_strings_t *left, const nsm_strings_t *right, co
         }
         const uint32_t resident = (uint32_t)sm_count();
         const uint32_t grid = (uint32_t)(n_units < resident ? n_units : resident);
+        p.unit_counter = next_unit_counter(stream);
+        if (!p.unit_counter) {
+            set_error("unit counter: %s", cudaGetErrorString(cudaGetLastError()));
+            return NSM_ERR_CUDA;
+        }
         int rc;
         switch (w_inst) {
             case 1: rc = launch_flat<1>(p, smem, grid, stream); break;

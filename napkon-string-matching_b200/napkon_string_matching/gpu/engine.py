@@ -105,6 +105,10 @@ class Engine:
         # (>= 2 packets per warp and unit), else 16-byte pairs; "coded" / True or "packets": that
         # format for every token-set job; False: always 16-byte pairs
         self.compact = "auto"
+        # results of large jobs that go to the host: the kernels store the records STRAIGHT into the
+        # engine's page-locked host arena (zero-copy stores over PCIe/C2C) — no device arena, no
+        # device->host copy to wait for, no host round trip per row block; see _run_jobs_direct
+        self.direct_host = True
         self._buffers: Dict[str, torch.Tensor] = {}
         self.launches = 0           # kernels of ours launched so far
         self.time_kernels = False   # bracket every comparison kernel with CUDA events
@@ -235,6 +239,8 @@ class Engine:
         ``PAIR_DTYPE`` arrays."""
         # the C ABI launches on the calling thread's current device: make it this engine's
         with torch.cuda.device(self.device):
+            if to_host and self.direct_host and self.pipeline_d2h and capacity is None:
+                return self._run_jobs_direct(jobs, copy, decode)
             return self._run_jobs(jobs, capacity, to_host, copy, decode)
 
     def _mark(self, label: str) -> None:
@@ -487,6 +493,303 @@ class Engine:
             dictionary = pin[dict_host[j]:dict_host[j] + dict_bytes].numpy().view(np.uint64) \
                 if (to_host and j in dict_host) else None
             rec = Records(views, info["count"] if to_host else 0, job.left.perm, job.right.perm, dictionary)
+            outs.append(rec.decode(copy=copy) if decode else rec)
+        return outs
+
+    # ------------------------------------------------------------------ the job, records stored by the kernels
+    def _run_jobs_direct(self, jobs: List["Job"], copy: bool, decode: bool = True):
+        """``run_jobs(to_host=True)`` without device arenas for the large jobs.
+
+        A job of PIPELINE_MIN_PAIRS item pairs or more runs as a PROBE (its first 512 left rows,
+        16-byte pairs into a small device arena) and a REST launch whose ``out_pairs`` is the
+        engine's page-locked host arena itself: the probe's kept-pair density sizes that region and
+        picks the record format; the kernel's 16-byte vector stores of whole packets cross the
+        link as they are produced.  All probes are launched first (one wait), then all rests back
+        to back (one wait): the GPU never idles on a host decision, nothing queues behind a bulk
+        copy, and the step ends when the last kernel does.  Smaller jobs take one launch into a
+        device arena and one copy.  An arena that turns out too small is counted exactly by the
+        kernel and that block is run again."""
+        import time
+
+        stream = torch.cuda.current_stream(self.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        copy_stream = self._copy_stream
+        self._mark("run_jobs begin")
+        rec_bytes, entry_records = nsmlib.RECORD_BYTES, nsmlib.ENTRY_RECORDS
+        dict_bytes = nsmlib.DICT_SLOTS * 8
+        n_ctl = 2 * max(1, len(jobs))
+        ctl = self._arena("ctl_direct", 64 * n_ctl, pinned=False)
+        ctl_pin = self._arena("ctl_direct_pin", 64 * n_ctl, pinned=True)
+        i_kept = nsmlib.STAT_NAMES.index("kept")
+
+        def n_units(rows: int, n_right: int) -> int:
+            return -(-rows // nsmlib.UNIT_LEFT) * -(-n_right // nsmlib.UNIT_RIGHT)
+
+        def entries_for(mode: int, records: float, rows: int, n_right: int) -> int:
+            if mode != nsmlib.OUT_PAIRS:   # full packets + at most one partial per warp and unit
+                return int(records / entry_records[mode]) + 4 * n_units(rows, n_right) + 64
+            return int(records) + 4096
+
+        def launch(job, rb, re_, mode, out_ptr, cap, slot, dict_ptr=None, exc_ptr=None, exc_cap=0):
+            fn = self.lib.nsm_jaccard_allpairs if job.left.kind == "sets" else self.lib.nsm_qratio_allpairs
+            c = ctl.data_ptr() + 64 * slot
+            coded = (dict_ptr, exc_ptr, exc_cap, c + 56) if mode == nsmlib.OUT_CODED else (None, None, 0, None)
+            cjob = nsmlib.NsmJob(rb, re_, int(job.flat), int(job.cat_mode), float(job.threshold),
+                                 job.l_cat.data_ptr() if job.l_cat is not None else None,
+                                 job.r_cat.data_ptr() if job.r_cat is not None else None,
+                                 out_ptr, cap, c, c + 8, c + 16, mode, 0, *coded)
+            if self.time_kernels:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+            nsmlib.check(fn(C.byref(job.left.struct), C.byref(job.right.struct), C.byref(cjob),
+                            C.c_void_p(stream.cuda_stream)))
+            if self.time_kernels:
+                e1.record(stream)
+                self._timed.append((e0, e1))
+            self.launches += self.lib.nsm_last_launch_count()
+            nsmlib.check(self.lib.nsm_publish(c, ctl_pin.data_ptr() + 64 * slot, 64,
+                                              C.c_void_p(stream.cuda_stream)))
+            self.launches += 1
+
+        def counters(slot: int, mode: int):
+            words = ctl_pin.numpy().view(np.uint64)[8 * slot: 8 * slot + 8]
+            count, flags = int(words[0]), int(words[1]) & 0xffffffff
+            stats = [int(x) for x in words[2:2 + nsmlib.N_STATS]]
+            if mode == nsmlib.OUT_PAIRS:
+                stats[i_kept] = count
+            return count, flags, stats, (int(words[7]) if mode == nsmlib.OUT_CODED else 0)
+
+        def account(info, count, flags, stats, n_exc, mode):
+            info["count"] += stats[i_kept]
+            info["flags"] |= flags & ~nsmlib.FLAG_OVERFLOW
+            info["blocks"] += 1
+            for name, v in zip(nsmlib.STAT_NAMES, stats):
+                info["stats"][name] += v
+            if mode != nsmlib.OUT_PAIRS:
+                info["packets"] += count
+                info["uncoded"] += n_exc
+
+        infos, plans = [], []
+        for j, job in enumerate(jobs):
+            if job.left.kind != job.right.kind:
+                raise TypeError("left and right must be packed for the same score function")
+            begin, end = job.rows if job.rows is not None else (0, job.left.n_items)
+            infos.append({"count": 0, "flags": 0, "reruns": 0, "blocks": 0, "d2h_bytes": 0,
+                          "packets": 0, "uncoded": 0, "stats": dict.fromkeys(nsmlib.STAT_NAMES, 0),
+                          "item_pairs": max(0, end - begin) * job.right.n_items, "parts": []})
+            rows = end - begin
+            if rows <= 0 or not job.right.n_items:
+                plans.append(None)
+                continue
+            forced = nsmlib.OUT_PAIRS
+            if job.left.kind == "sets" and self.compact in (True, "coded", "packets"):
+                forced = nsmlib.OUT_PACKETS if self.compact == "packets" else nsmlib.OUT_CODED
+            # the probe: four 512-row chunks.  Token-set cohorts are stored in level-count chunks laid
+            # out in bit-reversed order (pack.chunked_level_order), so four consecutive chunks hold
+            # the cohort's mix of level counts.  It already runs in the compact format (a sparse
+            # result costs it at most one packet per warp and unit).
+            big = rows >= 8 * nsmlib.UNIT_LEFT and rows * job.right.n_items >= self.PIPELINE_MIN_PAIRS
+            probe_mode = forced
+            if big and job.left.kind == "sets" and self.compact == "auto":
+                probe_mode = nsmlib.OUT_CODED
+            plans.append({"begin": begin, "end": end, "forced": forced, "big": big,
+                          "first_mode": probe_mode if big else forced,
+                          "cut": begin + 4 * nsmlib.UNIT_LEFT if big else end})
+        self.last_infos = infos
+
+        # ---- phase 1: probes of the big jobs, whole small jobs; 16-byte pairs into device arenas ----
+        def first_capacity(rows, n_right, mode):
+            return max(entries_for(mode, min(1 << 24, max(1 << 16, rows * n_right // 8)), rows, n_right), 1 << 16)
+
+        def run_first(js, caps):
+            for j in js:
+                job, pl = jobs[j], plans[j]
+                mode = pl["first_mode"]
+                dev = self._arena(f"first{j}", caps[j] * rec_bytes[mode], pinned=False)
+                pl["first_cap"] = dev.numel() // rec_bytes[mode]
+                extra = {}
+                if mode == nsmlib.OUT_CODED:
+                    if "dict" not in pl:   # one dictionary per result, shared by all its launches
+                        pl["dict"] = torch.empty(dict_bytes, dtype=torch.uint8, device=self.device)
+                        nsmlib.check(self.lib.nsm_dict_reset(pl["dict"].data_ptr(), C.c_void_p(stream.cuda_stream)))
+                    exc = self._arena(f"first_exc{j}", max(1 << 16, pl["first_cap"] * entry_records[mode] // 16) * 16,
+                                      pinned=False)
+                    extra = dict(dict_ptr=pl["dict"].data_ptr(), exc_ptr=exc.data_ptr(), exc_cap=exc.numel() // 16)
+                launch(job, pl["begin"], pl["cut"], mode, dev.data_ptr(), pl["first_cap"], 2 * j, **extra)
+            stream.synchronize()
+
+        live = [j for j, pl in enumerate(plans) if pl is not None]
+        caps = {j: first_capacity(plans[j]["cut"] - plans[j]["begin"], jobs[j].right.n_items,
+                                  plans[j]["first_mode"]) for j in live}
+        todo = list(live)
+        while todo:
+            run_first(todo, caps)
+            again = []
+            for j in todo:
+                count, flags, stats, n_exc = counters(2 * j, plans[j]["first_mode"])
+                if flags & nsmlib.FLAG_OVERFLOW:   # `count` is exact: run it again with that size
+                    infos[j]["reruns"] += 1
+                    caps[j] = int(count * 1.02) + 1024
+                    if plans[j]["first_mode"] == nsmlib.OUT_CODED:
+                        self._buffers.pop(f"first_exc{j}", None)
+                        self._arena(f"first_exc{j}", (int(n_exc * 1.1) + 1024) * 16, pinned=False)
+                    again.append(j)
+                else:
+                    plans[j]["first"] = (count, flags, stats, n_exc)
+            todo = again
+        self._mark("probes and small jobs done")
+
+        # ---- phase 2: host regions for everything, then the rests straight into them ----
+        align = lambda x: (x + 255) & ~255   # noqa: E731
+        layout, need = [], 0
+        for j in live:
+            job, pl = jobs[j], plans[j]
+            count, flags, stats, n_exc = pl["first"]
+            mode = pl["first_mode"]
+            pl["first_off"] = need
+            need = align(need + count * rec_bytes[mode])
+            if n_exc:
+                pl["first_exc_off"] = need
+                need = align(need + n_exc * 16)
+            if not pl["big"]:
+                if mode == nsmlib.OUT_CODED:
+                    pl["dict_off"] = need
+                    need = align(need + dict_bytes)
+                continue
+            kept = stats[i_kept]
+            n_right = job.right.n_items
+            density = kept / max(1, (pl["cut"] - pl["begin"]) * n_right)
+            rest_rows = pl["end"] - pl["cut"]
+            expect = density * rest_rows * n_right
+            r_mode = pl["forced"]
+            if (self.compact == "auto" and job.left.kind == "sets" and
+                    density * nsmlib.UNIT_LEFT * 32 >= 2 * nsmlib.CPACKET_RECORDS):
+                r_mode = nsmlib.OUT_CODED   # >= two packets per warp and unit
+            limit = self.max_pairs_per_block
+            # strings are stored by rising length: the probe rows are the shortest ones
+            margin = (1.25 if expect > 1e6 else 2.0) if job.left.kind == "sets" else 3.0
+            n_parts = int(max(1, -(-(expect * margin) // limit)))
+            step = -(-rest_rows // n_parts)
+            step = -(-step // nsmlib.UNIT_LEFT) * nsmlib.UNIT_LEFT
+            cuts = list(range(pl["cut"], pl["end"], step)) + [pl["end"]]
+            pl["rest_mode"], pl["rest"] = r_mode, []
+            if r_mode == nsmlib.OUT_CODED and "dict" not in pl:
+                pl["dict"] = torch.empty(dict_bytes, dtype=torch.uint8, device=self.device)
+                nsmlib.check(self.lib.nsm_dict_reset(pl["dict"].data_ptr(), C.c_void_p(stream.cuda_stream)))
+            if "dict" in pl:
+                pl["dict_off"] = need
+                need = align(need + dict_bytes)
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                if b <= a:
+                    continue
+                cap = entries_for(r_mode, density * (b - a) * n_right * margin + 4096, b - a, n_right)
+                blk = {"rb": a, "re": b, "cap": cap, "off": need}
+                need = align(need + cap * rec_bytes[r_mode])
+                if r_mode == nsmlib.OUT_CODED:
+                    blk["exc_cap"] = int(density * (b - a) * n_right * 0.1) + (1 << 14)
+                    blk["exc_off"] = need
+                    need = align(need + blk["exc_cap"] * 16)
+                pl["rest"].append(blk)
+        pin = self._buffers.get("pin")
+        if pin is None or pin.numel() < need:
+            self._buffers.pop("pin", None)
+            pin = self._buffers["pin"] = torch.empty(max(need, 1 << 20), dtype=torch.uint8).pin_memory()
+        base = pin.data_ptr()
+        self._mark("host arena ready")
+
+        # the first launches' records: exact-size copies on the copy stream (they are small)
+        with torch.cuda.stream(copy_stream):
+            for j in live:
+                pl = plans[j]
+                count, flags, stats, n_exc = pl["first"]
+                mode = pl["first_mode"]
+                n_bytes = count * rec_bytes[mode]
+                if n_bytes:
+                    pin[pl["first_off"]:pl["first_off"] + n_bytes].copy_(self._buffers[f"first{j}"][:n_bytes],
+                                                                         non_blocking=True)
+                    infos[j]["parts"].append((pl["first_off"], n_bytes, mode))
+                if n_exc:
+                    pin[pl["first_exc_off"]:pl["first_exc_off"] + n_exc * 16].copy_(
+                        self._buffers[f"first_exc{j}"][:n_exc * 16], non_blocking=True)
+                    infos[j]["parts"].append((pl["first_exc_off"], n_exc * 16, nsmlib.OUT_PAIRS))
+                infos[j]["d2h_bytes"] += n_bytes + n_exc * 16 + (dict_bytes if "dict" in pl else 0)
+                account(infos[j], count, flags, stats, n_exc, mode)
+
+        slots = {}
+        n_slot = 0
+        pending = [(j, blk) for j in live if plans[j]["big"] for blk in plans[j]["rest"]]
+        while pending:
+            ctl_rest = self._arena("ctl_rest", 64 * len(pending), pinned=False)
+            ctl_rest_pin = self._arena("ctl_rest_pin", 64 * len(pending), pinned=True)
+            ctl, ctl_pin = ctl_rest, ctl_rest_pin   # launch() / counters() address these
+            for slot, (j, blk) in enumerate(pending):
+                job, pl = jobs[j], plans[j]
+                mode = pl["rest_mode"]
+                extra = {}
+                if mode == nsmlib.OUT_CODED:
+                    extra = dict(dict_ptr=pl["dict"].data_ptr(), exc_ptr=base + blk["exc_off"], exc_cap=blk["exc_cap"])
+                launch(job, blk["rb"], blk["re"], mode, base + blk["off"], blk["cap"], slot, **extra)
+            self._mark("rests launched")
+            stream.synchronize()
+            self._mark("rests done")
+            again = []
+            for slot, (j, blk) in enumerate(pending):
+                pl = plans[j]
+                mode = pl["rest_mode"]
+                count, flags, stats, n_exc = counters(slot, mode)
+                if flags & nsmlib.FLAG_OVERFLOW:
+                    infos[j]["reruns"] += 1
+                    again.append((j, dict(blk, cap=int(count * 1.02) + 1024, exc_cap=int(n_exc * 1.1) + 1024)))
+                    continue
+                n_bytes = count * rec_bytes[mode]
+                if n_bytes:
+                    infos[j]["parts"].append((blk["off"], n_bytes, mode))
+                if n_exc:
+                    infos[j]["parts"].append((blk["exc_off"], n_exc * 16, nsmlib.OUT_PAIRS))
+                infos[j]["d2h_bytes"] += n_bytes + n_exc * 16
+                account(infos[j], count, flags, stats, n_exc, mode)
+            if again:
+                # regions for the repeated blocks behind everything else; the arena may have to grow,
+                # which is safe now: no kernel is writing to it
+                copy_stream.synchronize()
+                fill = need
+                for j, blk in again:
+                    mode = plans[j]["rest_mode"]
+                    blk["off"] = need
+                    need = align(need + blk["cap"] * rec_bytes[mode])
+                    if mode == nsmlib.OUT_CODED:
+                        blk["exc_off"] = need
+                        need = align(need + blk["exc_cap"] * 16)
+                if pin.numel() < need:
+                    grown = torch.empty(need, dtype=torch.uint8).pin_memory()
+                    grown[:fill].copy_(pin[:fill])
+                    self._buffers["pin"] = pin = grown
+                    base = pin.data_ptr()
+            pending = again
+        for j in live:   # the dictionaries as the last launch left them (queued behind the kernels)
+            pl = plans[j]
+            if "dict" in pl:
+                pin[pl["dict_off"]:pl["dict_off"] + dict_bytes].copy_(pl["dict"], non_blocking=True)
+        copy_stream.synchronize()
+        stream.synchronize()
+        self._mark("copies done")
+        if self.time_kernels:
+            for e0, e1 in self._timed:
+                self.kernel_ms += e0.elapsed_time(e1)
+                self.kernel_launches_timed += 1
+            self._timed.clear()
+
+        outs = []
+        wire = (PAIR_DTYPE, nsmlib.PACKET_DTYPE, nsmlib.CPACKET_DTYPE)
+        for j, (job, info) in enumerate(zip(jobs, infos)):
+            parts = info.pop("parts")
+            views = [(mode, pin[lo:lo + n].numpy().view(wire[mode])) for lo, n, mode in parts]
+            pl = plans[j]
+            dictionary = None
+            if pl is not None and "dict_off" in pl:
+                dictionary = pin[pl["dict_off"]:pl["dict_off"] + dict_bytes].numpy().view(np.uint64)
+            rec = Records(views, info["count"], job.left.perm, job.right.perm, dictionary)
             outs.append(rec.decode(copy=copy) if decode else rec)
         return outs
 

@@ -18,7 +18,7 @@ MARKS = [("warp_intersect_count", "uint32_t warp_intersect_count("),
          ("bound_intersection", "uint32_t bound_intersection("),
          ("kernel prologue", "jaccard_allpairs_kernel(const JaccardParams p)"),
          ("flush_out", "auto flush_out"), ("level accessors", "auto left_level"),
-         ("unit staging (TMA, any words)", "for (uint32_t unit = blockIdx.x"),
+         ("unit staging (TMA, any words)", "while (unit < n_units) {"),
          ("stage A any", "// ---- stage A:"), ("stage B bound", "// ---- stage B:"),
          ("stage C exact", "// ---- stage C:"), ("compaction", "// ---- threshold compaction"),
          ("epilogue", "    if (!packets && !coded) flush_out();")]

@@ -384,6 +384,7 @@ def test_pipelined_row_blocks_give_the_same_records(engine):
     dl, dr = engine.upload(pl), engine.upload(pr)
     key = lambda a: a[np.lexsort((a["right"], a["left"]))]
     engine.PIPELINE_MIN_PAIRS = 1     # instance overrides of the class constants, dropped below
+    engine.direct_host = False        # the device-arena pipeline (Engine._run_jobs)
     try:
         for thr in (0.1, 0.7):
             engine.pipeline_d2h = False
@@ -400,7 +401,7 @@ def test_pipelined_row_blocks_give_the_same_records(engine):
             part = key(engine.all_pairs(dl, dr, thr, rows=(1000, 19000)))
             assert np.array_equal(part, want[(want["left"] >= 1000) & (want["left"] < 19000)])
     finally:
-        engine.pipeline_d2h = True
+        engine.pipeline_d2h = engine.direct_host = True
         for name in ("PIPELINE_BLOCK_BYTES", "PIPELINE_MIN_PAIRS"):
             engine.__dict__.pop(name, None)
 

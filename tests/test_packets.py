@@ -113,6 +113,7 @@ def test_probe_sized_pipeline_has_no_reruns(engine, monkeypatch):
     monkeypatch.setattr(engine, "PIPELINE_MIN_PAIRS", 1 << 20)
     monkeypatch.setattr(engine, "PIPELINE_BLOCK_BYTES", 4 << 20)   # several blocks
     old = engine.compact
+    monkeypatch.setattr(engine, "direct_host", False)   # the device-arena pipeline (Engine._run_jobs)
     try:
         engine.compact = "auto"
         piped = engine.all_pairs(dl, dr, 0.1)
@@ -201,3 +202,61 @@ def test_sharded_run_jobs_on_real_gpus(tmp_path, compact):
         env={**os.environ, "OMP_NUM_THREADS": "4", "NSM_TEST_COMPACT": compact})
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert res.stdout.count("ok") == world, res.stdout
+
+
+@pytest.mark.gpu
+def test_records_stored_straight_into_the_host_arena(engine, monkeypatch):
+    """Engine._run_jobs_direct: a probe of four chunks, then the rest of the rows with the pinned host
+    arena as the kernel's output buffer.  Dense results arrive as coded packets, sparse ones as
+    16-byte pairs; a rest that keeps far more than its probe announced is counted exactly and run
+    again; several jobs share one call; a row range and a result beyond max_pairs_per_block (rest
+    split into parts) give the same records."""
+    from napkon_string_matching.gpu.engine import Job
+
+    assert engine.direct_host
+    pl, pr = _tokenid_packs(9000, 3000)
+    dl, dr = engine.upload(pl), engine.upload(pr)
+    monkeypatch.setattr(engine, "PIPELINE_MIN_PAIRS", 1 << 62)
+    plain = engine.all_pairs(dl, dr, 0.1)
+    assert engine.last_info["blocks"] == 1
+    monkeypatch.setattr(engine, "PIPELINE_MIN_PAIRS", 1 << 20)
+    old = engine.compact, engine.max_pairs_per_block
+    try:
+        engine.compact = "auto"
+        direct = engine.all_pairs(dl, dr, 0.1)
+        info = dict(engine.last_info)
+        assert info["blocks"] == 2 and info["reruns"] == 0 and info["packets"] > 0
+        assert info["count"] == len(plain) and info["d2h_bytes"] < 6 * len(plain) + nsmlib.DICT_SLOTS * 8
+        assert_same_triples((direct["left"], direct["right"], direct["score"]),
+                            (plain["left"], plain["right"], plain["score"]))
+        # sparse: the rest goes out as 16-byte pairs (only the probe is in packets)
+        sparse = engine.all_pairs(dl, dr, 0.6)
+        want = plain[plain["score"] >= 0.6]
+        assert engine.last_info["reruns"] == 0 and engine.last_info["d2h_bytes"] < 16 * len(want) + (4 << 20)
+        assert_same_triples((sparse["left"], sparse["right"], sparse["score"]),
+                            (want["left"], want["right"], want["score"]))
+        # a row range, several jobs in one call, and a result split by max_pairs_per_block
+        part = engine.all_pairs(dl, dr, 0.1, rows=(700, 8123))
+        sel = (plain["left"] >= 700) & (plain["left"] < 8123)
+        assert_same_triples((part["left"], part["right"], part["score"]),
+                            (plain["left"][sel], plain["right"][sel], plain["score"][sel]))
+        engine.max_pairs_per_block = len(plain) // 3
+        outs = engine.run_jobs([Job(dl, dr, 0.1), Job(dl, dr, 0.6), Job(dl, dr, 0.1, rows=(0, 600))])
+        assert engine.last_infos[0]["blocks"] >= 4
+        for got, w in zip(outs, (plain, want, plain[plain["left"] < 600])):
+            assert_same_triples((got["left"], got["right"], got["score"]), (w["left"], w["right"], w["score"]))
+    finally:
+        engine.compact, engine.max_pairs_per_block = old
+    # probe rows that keep nothing: the rest overflows its (minimal) region, is counted and run again
+    lens, flat = syn.token_id_level_sets(9000, syn.SEED_LEFT)
+    lens = lens.copy(); flat = flat.copy()
+    head = int(lens[:2048].sum())
+    flat[:head] = 29999 - (flat[:head] % 64)        # ids the right side (almost) never holds
+    odd = pack.pack_suffix_id_sets(lens, flat, 30000)
+    do = engine.upload(odd)
+    monkeypatch.setattr(engine, "PIPELINE_MIN_PAIRS", 1 << 62)
+    want = engine.all_pairs(do, dr, 0.1)
+    monkeypatch.setattr(engine, "PIPELINE_MIN_PAIRS", 1 << 20)
+    got = engine.all_pairs(do, dr, 0.1)
+    assert engine.last_info["reruns"] >= 1 and engine.last_info["count"] == len(want)
+    assert_same_triples((got["left"], got["right"], got["score"]), (want["left"], want["right"], want["score"]))
