@@ -741,7 +741,12 @@ def measure(prep: Prepared, steps: int, warmup: int, rank: int, world: int, int_
     gc.enable()
     timed_trace = None
     if eng.trace:
-        timed_trace = [(round((t - eng.trace[0][0]) * 1e3, 2), label) for t, label in eng.trace][:40]
+        timed_trace = [(round((t - eng.trace[0][0]) * 1e3, 2), label) for t, label in eng.trace]
+        out_dir = os.environ.get("NSM_BENCH_TRACE_DIR")
+        if out_dir:   # every rank's marks of the timed region, to see which rank a slow step waited for
+            pathlib.Path(out_dir, f"trace_{prep.config['workload']}_rank{rank}.json").write_text(
+                json.dumps({"steps_ms": list(timed.steps_ms), "marks": timed_trace}))
+        timed_trace = timed_trace[:40]
     t1 = time.time()
     eng.time_kernels = False
     e2e_kernel_ms, e2e_kernel_launches, e2e_launches = eng.kernel_ms, eng.kernel_launches_timed, eng.launches - launches0

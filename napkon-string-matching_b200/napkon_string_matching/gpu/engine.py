@@ -359,7 +359,7 @@ class Engine:
             pin = self._buffers.get("pin")
             if pin is None or pin.numel() < fill + n_bytes:
                 copy_stream.synchronize()
-                grown = torch.empty(max(fill + n_bytes, (pin.numel() * 3 // 2) if pin is not None else 0),
+                grown = torch.empty(max((fill + n_bytes) * 5 // 4, (pin.numel() * 3 // 2) if pin is not None else 0),
                                     dtype=torch.uint8).pin_memory()
                 if fill:
                     grown[:fill].copy_(pin[:fill])
@@ -693,8 +693,10 @@ class Engine:
                 pl["rest"].append(blk)
         pin = self._buffers.get("pin")
         if pin is None or pin.numel() < need:
+            # page-locking is slow (hundreds of ms per GB, more inside a VM) and the need varies a
+            # little from call to call (which scores find a dictionary slot is a race): headroom
             self._buffers.pop("pin", None)
-            pin = self._buffers["pin"] = torch.empty(max(need, 1 << 20), dtype=torch.uint8).pin_memory()
+            pin = self._buffers["pin"] = torch.empty(max(need + need // 4, 1 << 20), dtype=torch.uint8).pin_memory()
         base = pin.data_ptr()
         self._mark("host arena ready")
 
@@ -762,7 +764,7 @@ class Engine:
                         blk["exc_off"] = need
                         need = align(need + blk["exc_cap"] * 16)
                 if pin.numel() < need:
-                    grown = torch.empty(need, dtype=torch.uint8).pin_memory()
+                    grown = torch.empty(need + need // 4, dtype=torch.uint8).pin_memory()
                     grown[:fill].copy_(pin[:fill])
                     self._buffers["pin"] = pin = grown
                     base = pin.data_ptr()
