@@ -187,6 +187,7 @@ __device__ __forceinline__ ulonglong2 warp_intersect_steps(const uint32_t *__res
         const uint32_t tn = na; na = nb; nb = tn;
     }
     const unsigned lane = lane_id();
+    const uint64_t ones = 0x0101010101010101ull;
     for (uint32_t base = 0; base < na; base += 32) {
         const bool valid = base + lane < na;
         const uint32_t x = valid ? __ldg(a + base + lane) : 0u;
@@ -209,7 +210,6 @@ __device__ __forceinline__ ulonglong2 warp_intersect_steps(const uint32_t *__res
         }
         // my id counts for every step t >= d: a one in the bytes d-1 .. 15, summed over the warp
         // (at most 32 per byte and chunk, at most 255 in total: bytes never carry into each other)
-        const uint64_t ones = 0x0101010101010101ull;
         const uint64_t lo = d <= 8 ? ones << (8 * (d - 1)) : 0ull;
         const uint64_t hi = d <= 8 ? ones : (d <= 16 ? ones << (8 * (d - 9)) : 0ull);
         cnt.x += (uint64_t)__reduce_add_sync(FULL_MASK, (uint32_t)lo) |

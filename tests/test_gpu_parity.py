@@ -373,6 +373,35 @@ def test_jaccard_two_shared_bits_filter_vs_oracle(engine, vocab, max_k, per_part
     assert kept > 0
 
 
+@pytest.mark.parametrize("vocab,max_k,per_part,nested", [(90, 9, 2, True), (400, 10, 3, True), (3000, 6, 8, True),
+                                                          (20000, 11, 2, True), (500, 8, 3, False)])
+def test_jaccard_coarse_first_half_vs_oracle(engine, vocab, max_k, per_part, nested):
+    """Low thresholds (depth D >= 3) over nested levels that all lie in the slots run stage B with
+    the COARSE first half (jaccard.cu, SPLIT == 0) and the stage A tiles drawn from a shared
+    counter; deep schedules (K up to 11: one level beyond the slots' ten steps), dense and sparse
+    vocabularies and a cohort whose levels are NOT nested (coarse half off) must match the oracle."""
+    rng = np.random.default_rng(3 * vocab + max_k)
+
+    def items(n):
+        out = []
+        for _ in range(n):
+            parts = [[f"w{int(x)}" for x in rng.zipf(1.15, size=int(rng.integers(1, per_part + 1))) % vocab]
+                     for _ in range(int(rng.integers(1, max_k + 1)))]
+            levels = [sorted({w for part in parts[-j:] for w in part}) for j in range(1, len(parts) + 1)]
+            if not nested and len(levels) > 2:
+                levels[1] = sorted(set(levels[1]) ^ {f"w{int(rng.integers(0, vocab))}", levels[0][0]}) or levels[1]
+            out.append(levels)
+        return out
+
+    pl, pr = pack.pack_sets(items(700), items(640))
+    assert pl.nested == nested and max(pl.max_levels, pr.max_levels) <= min(pl.n_slots, pr.n_slots) + 1
+    kept = 0
+    for thr in (0.01, 0.03, 0.0625, 0.1, 0.12, 0.2, 0.24):
+        out, info = check_against_oracle(engine, pl, pr, thr)
+        kept += len(out)
+    assert kept > 1000
+
+
 def test_pipelined_row_blocks_give_the_same_records(engine):
     """Results that go to the host are produced as a probe block plus row blocks sized by the
     probe's density (Engine._run_jobs), so that the copy-out overlaps the remaining kernels.  The
