@@ -23,3 +23,19 @@ for n in (50_000, 1_000_000):
         (c,) = eng.device_packer.pack([raw], 30000, rank=None)
         torch.cuda.synchronize(); t_dev = time.time() - t0
     print(f"tokenids n={n}: host pack {t_host*1e3:.0f} ms, device pack {t_dev*1e3:.1f} ms")
+# strings: default_process + pack_strings on the host against DeviceStringPacker (host join / encode / numpy
+# per level included in the device figure; the kernels are two of its stages)
+from napkon_string_matching.text.process import default_process
+vocab = syn.vocabulary()
+for n in (20_000, 200_000):
+    left = [[s] for s in syn.question_strings(n, syn.SEED_LEFT, vocab)]
+    right = [[s] for s in syn.question_strings(n, syn.SEED_RIGHT, vocab)]
+    t0 = time.time()
+    hp = pack.pack_strings([[default_process(x) for x in lv] for lv in left], [[default_process(x) for x in lv] for lv in right])
+    t_host = time.time() - t0
+    sp = dp.DeviceStringPacker(eng)
+    for rep in range(3):
+        torch.cuda.synchronize(); t0 = time.time()
+        dl, dr = sp.pack([left, right])
+        torch.cuda.synchronize(); t_dev = time.time() - t0
+    print(f"strings 2 x n={n}: host default_process + pack_strings {t_host*1e3:.0f} ms, DeviceStringPacker.pack {t_dev*1e3:.0f} ms")
