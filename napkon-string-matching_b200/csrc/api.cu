@@ -85,7 +85,7 @@ int prepare_job(const nsm_job_t *job, uint32_t n_left, cudaStream_t stream) {
 
 // Unit counters: a small per-device pool, one entry per launch in flight (round robin), zeroed on
 // the launch's stream right before it.  Persistent kernels draw their work units from them.
-constexpr int N_UNIT_COUNTERS = 256;
+constexpr int N_UNIT_COUNTERS = 4096;   // far more than the launches a process keeps in flight
 __device__ uint32_t g_unit_counters[N_UNIT_COUNTERS];
 
 uint32_t *next_unit_counter(cudaStream_t stream) {

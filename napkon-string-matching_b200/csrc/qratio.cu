@@ -64,9 +64,13 @@ qratio_allpairs_kernel(const QratioParams p) {
         return m;
     };
 
+    // units are drawn from a device counter, in falling order of cost (both sides are stored by
+    // rising length), as in qratio_flat.cu
     const uint32_t n_units = p.n_lgroups * p.n_rblocks;
-    for (uint32_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-        const uint32_t rb = unit / p.n_lgroups, lgroup = unit - rb * p.n_lgroups;
+    uint32_t unit = blockIdx.x;
+    while (unit < n_units) {
+        const uint32_t unit_rev = n_units - 1u - unit;
+        const uint32_t rb = unit_rev / p.n_lgroups, lgroup = unit_rev - rb * p.n_lgroups;
         const uint32_t r = p.r_begin + rb * nthr + tid;
         const bool r_valid = r < p.r_end;
         uint32_t rg0 = 0, kr = 0;
@@ -79,7 +83,10 @@ qratio_allpairs_kernel(const QratioParams p) {
         uint32_t cur_slot = 0xffffffffu, m = 0;
         if (LEVELS) {
             __syncthreads();  // s_misc of the previous unit consumed
-            if (tid == 0) s_misc[0] = 0;
+            if (tid == 0) {
+                s_misc[0] = 0;
+                s_misc[1] = p.unit_counter ? gridDim.x + atomicAdd(p.unit_counter, 1u) : unit + gridDim.x;
+            }
             __syncthreads();
             uint32_t k = kr;
             for (int o = 16; o; o >>= 1) k = max(k, __shfl_xor_sync(FULL_MASK, k, o));
@@ -186,6 +193,7 @@ qratio_allpairs_kernel(const QratioParams p) {
                 }
             }
         }
+        unit = LEVELS ? s_misc[1] : unit + gridDim.x;   // drawn at the top of this unit (see there)
     }
     if (p.job.out_stats) {
         for (int o = 16; o; o >>= 1) st_evals += __shfl_xor_sync(FULL_MASK, st_evals, o);
@@ -274,6 +282,11 @@ static int levels_launch(const nsm_strings_t *left, const nsm_strings_t *right, 
         }
         const uint32_t resident = (uint32_t)sm_count();
         const uint32_t grid = (uint32_t)(n_units < resident ? n_units : resident);
+        p.unit_counter = next_unit_counter(stream);
+        if (!p.unit_counter) {
+            set_error("unit counter: %s", cudaGetErrorString(cudaGetLastError()));
+            return NSM_ERR_CUDA;
+        }
         if (int rc = dispatch_levels(w_inst, p, smem, grid, stream)) return rc;
     }
     return NSM_OK;

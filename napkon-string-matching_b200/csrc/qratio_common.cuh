@@ -24,6 +24,7 @@ struct QratioParams {
     uint32_t n_alpha;   // rows of the mask table
     uint32_t r_begin, r_end;  // the right items of this launch (one word-count class)
     uint32_t swap_out;        // 1: emit (right, left): the caller swapped the sides
+    uint32_t *unit_counter;   // device counter the CTAs draw their units from; NULL: fixed stride
 };
 
 // qratio_flat.cu: items with one level each; right items [r_lo, r_hi) of the classes <= 8 words
