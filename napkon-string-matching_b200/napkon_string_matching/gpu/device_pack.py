@@ -297,6 +297,8 @@ class DeviceStringPacker:
         arr = np.ascontiguousarray(arr, dtype=dtype)
         if arr.size == 0:
             arr = np.zeros(1, dtype=dtype)
+        if not arr.flags.writeable:   # np.frombuffer over the encoded text: torch wants a writable source
+            arr = arr.copy()
         return torch.from_numpy(arr.view(np.uint8).reshape(-1)).to(self.device)
 
     def _stream(self):
