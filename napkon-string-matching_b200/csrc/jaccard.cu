@@ -357,7 +357,7 @@ jaccard_allpairs_kernel(const JaccardParams p) {
             info = __ldg(p.L.level_info + g);
             return make_ulonglong2(__ldg(p.L.level_head + g), __ldg(p.L.level_tail + g));
         }
-        const size_t at = (size_t)(min(t, SL) - 1) * p.L.slot_stride + item;
+        const uint32_t at = (min(t, SL) - 1) * p.L.slot_stride + item;   // < 2^32: checked by the host
         info = __ldg(p.L.slot_info + at);
         return __ldg(l_slot_ht + at);
     };
@@ -515,7 +515,7 @@ jaccard_allpairs_kernel(const JaccardParams p) {
             auto bound_step = [&](uint32_t t, uint32_t li, uint32_t rc, uint32_t kmax, float ub) {
                 // steps beyond kmax read a repeated level and get weight 0
                 const uint32_t sr = min(t, SR) - 1;
-                const size_t at = (size_t)(min(t, SL) - 1) * p.L.slot_stride + l0 + li;
+                const uint32_t at = (min(t, SL) - 1) * p.L.slot_stride + l0 + li;
                 const uint32_t ia = __ldg(p.L.slot_info + at), ib = s.r_info[sr][rc];
                 const uint32_t ih = bound_intersection(__ldg(l_slot_ht + at), ia, s.r_ht[sr][rc], ib,
                                                        exact_bits);
@@ -553,11 +553,11 @@ jaccard_allpairs_kernel(const JaccardParams p) {
                         // threshold, get the per-step bound of all T steps in the second half.
                         const uint32_t sl2 = min(2u, SL) - 1, sl3 = min(3u, SL) - 1, slT = min((uint32_t)J_UNROLL, SL) - 1;
                         const uint32_t sr2 = min(2u, SR) - 1, sr3 = min(3u, SR) - 1, srT = min((uint32_t)J_UNROLL, SR) - 1;
-                        const size_t item = (size_t)l0 + li;
-                        const ulonglong2 A2 = __ldg(l_slot_ht + (size_t)sl2 * p.L.slot_stride + item);
-                        const ulonglong2 AT = __ldg(l_slot_ht + (size_t)slT * p.L.slot_stride + item);
-                        const uint32_t iaT = __ldg(p.L.slot_info + (size_t)slT * p.L.slot_stride + item);
-                        const uint32_t ia3 = __ldg(p.L.slot_info + (size_t)sl3 * p.L.slot_stride + item);
+                        const uint32_t item = l0 + li;
+                        const ulonglong2 A2 = __ldg(l_slot_ht + (sl2 * p.L.slot_stride + item));
+                        const ulonglong2 AT = __ldg(l_slot_ht + (slT * p.L.slot_stride + item));
+                        const uint32_t iaT = __ldg(p.L.slot_info + (slT * p.L.slot_stride + item));
+                        const uint32_t ia3 = __ldg(p.L.slot_info + (sl3 * p.L.slot_stride + item));
                         const ulonglong2 B2 = s.r_ht[sr2][rc];
                         const bool share2 = ((A2.x & B2.x) | (A2.y & B2.y)) != 0;
                         const uint32_t ih = bound_intersection(AT, iaT, s.r_ht[srT][rc], s.r_info[srT][rc], exact_bits);
@@ -948,6 +948,11 @@ extern "C" int nsm_jaccard_allpairs(const nsm_sets_t *left, const nsm_sets_t *ri
     }
     if (left->max_levels > 0xffffu || right->max_levels > 0xffffu) {
         set_error("items with more than 65535 levels are not supported");
+        return NSM_ERR_UNSUPPORTED;
+    }
+    if ((uint64_t)left->n_slots * left->slot_stride > 0xffffffffull ||
+        (uint64_t)right->n_slots * right->slot_stride > 0xffffffffull) {
+        set_error("slot arrays beyond 2^32 entries are not supported");
         return NSM_ERR_UNSUPPORTED;
     }
     if (left->n_slots < 1 || left->n_slots > (uint32_t)J_SLOTS || right->n_slots < 1 ||
