@@ -49,7 +49,7 @@ struct QflatParams {
 };
 
 struct QflatLayout {
-    size_t pm, dmax, chr, hist, len, cat, misc, total;
+    size_t pm, dmax, chr, hist, len, cat, misc, surv, plen, pool, total;
 };
 
 __host__ __device__ inline QflatLayout qflat_layout(uint32_t n_rows, uint32_t words, uint32_t threads,
@@ -62,6 +62,9 @@ __host__ __device__ inline QflatLayout qflat_layout(uint32_t n_rows, uint32_t wo
     l.cat = o;  o += QF_TILE * 8;
     l.len = o;  o += QF_TILE * 4;
     l.misc = o; o += 16;
+    l.surv = o; o += (size_t)QF_MASK_WORDS * threads * 8;   // survivor bit masks of the batch, [word][thread]
+    l.plen = o; o += (size_t)threads * 4;                    // pattern length of every column
+    l.pool = o; o += 16 * 4;                                 // next work word of every bank-pair class
     l.dmax = o; o += ((size_t)table_len * 2 + 15) & ~(size_t)15;
     l.total = (o + 15) & ~(size_t)15;
     return l;
@@ -112,6 +115,9 @@ qratio_flat_kernel(const QflatParams p) {
     uint32_t *s_len = reinterpret_cast<uint32_t *>(smem_raw + lay.len);    // 0xffffffff: no level
     uint64_t *s_cat = reinterpret_cast<uint64_t *>(smem_raw + lay.cat);
     uint32_t *s_misc = reinterpret_cast<uint32_t *>(smem_raw + lay.misc);  // [0] longest text of the batch
+    uint64_t *s_surv = reinterpret_cast<uint64_t *>(smem_raw + lay.surv);
+    uint32_t *s_plen = reinterpret_cast<uint32_t *>(smem_raw + lay.plen);
+    uint32_t *s_pool = reinterpret_cast<uint32_t *>(smem_raw + lay.pool);
 
     unsigned long long *count = reinterpret_cast<unsigned long long *>(p.job.out_count);
     nsm_pair_t *out = static_cast<nsm_pair_t *>(p.job.out_pairs);
@@ -131,8 +137,8 @@ qratio_flat_kernel(const QflatParams p) {
     // the padding code's mask row stays zero for every pattern
     for (uint32_t x = 0; x < (uint32_t)W; ++x) s_pm[((size_t)pad_code * W + x) * nthr + tid] = 0;
 
-    auto step = [&](uint64_t (&S)[W], uint32_t c) {
-        const unsigned char *row = col + c * row_bytes;
+    auto step = [&](uint64_t (&S)[W], uint32_t c, const unsigned char *column) {
+        const unsigned char *row = column + c * row_bytes;
         uint64_t M[W], u[W], sum[W];
 #pragma unroll
         for (int x = 0; x < W; ++x) {
@@ -193,6 +199,7 @@ qratio_flat_kernel(const QflatParams p) {
             for (uint32_t b0 = 0; b0 < tn;) {
                 __syncthreads();  // previous batch fully consumed
                 if (tid == 0) s_misc[0] = 0;
+                if (tid < 16) s_pool[tid] = 0;   // phase 2's work counters (read behind the barriers below)
                 __syncthreads();
                 // lengths first: they size the batch
                 uint32_t my_max = 0;
@@ -279,59 +286,76 @@ qratio_flat_kernel(const QflatParams p) {
                     }
                 }
 
-                // ---- phase 2: every lane scores its own survivors, two per round ------------------
-                auto next_survivor = [&]() -> uint32_t {   // my lowest survivor, removed; bn (the dummy row): none
-                    uint32_t pick = bn;
-                    bool found = false;
+                // ---- phase 2: the survivors of the whole CTA, pooled per bank-pair class -----------
+                // Survivor counts differ up to 7x between the lanes of a warp (a string with rare letters
+                // has few histogram neighbours) and the batch ends when its fullest lane does, so the
+                // lists are pooled.  A lane may read ANY mask column whose bank pair is its own: columns
+                // c with c % 16 == lane % 16 (the 16 lanes of a half-warp then still hit 16 different
+                // bank pairs: no conflict).  The survivor words of those columns form the pool of the
+                // class; its 2 lanes per warp draw 64-survivor words from it through a shared counter.
+                // (the barrier at the top of the batch freed the pool arrays of the previous one)
 #pragma unroll
-                    for (int x = 0; x < QF_MASK_WORDS; ++x) {   // branch-free: the words stay in registers
-                        const bool take = !found && mask[x] != 0;
-                        const uint32_t b = (uint32_t)__ffsll((long long)mask[x]) - 1u;
-                        pick = take ? 64u * x + b : pick;
-                        mask[x] = take ? (mask[x] & (mask[x] - 1)) : mask[x];
-                        found |= take;
-                    }
-                    return pick;
-                };
-                while (__any_sync(FULL_MASK, n_pass != 0)) {
-                    const uint32_t li0 = next_survivor(), li1 = next_survivor();
-                    n_pass -= min(n_pass, 2u);
-                    const uint32_t n0 = li0 < bn ? s_len[li0] : 0u, n1 = li1 < bn ? s_len[li1] : 0u;
-                    const uint32_t trip = __reduce_max_sync(FULL_MASK, max(n0, n1));
-                    const uint2 *ta = reinterpret_cast<const uint2 *>(s_chr + li0 * stride);
-                    const uint2 *tb = reinterpret_cast<const uint2 *>(s_chr + li1 * stride);
-                    uint64_t Sa[W], Sb[W];
-#pragma unroll
-                    for (int x = 0; x < W; ++x) Sa[x] = Sb[x] = ~0ull;
-                    for (uint32_t j = 0; j < trip; j += 8) {
-                        const uint2 wa = ta[j >> 3], wb = tb[j >> 3];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            step(Sa, __byte_perm(wa.x, 0u, 0x4440u + q));
-                            step(Sb, __byte_perm(wb.x, 0u, 0x4440u + q));
+                for (int x = 0; x < QF_MASK_WORDS; ++x) s_surv[(uint32_t)x * nthr + tid] = mask[x];
+                s_plen[tid] = m;
+                if (__syncthreads_or(n_pass != 0)) {   // (a batch nobody survives, the rule at high thresholds, ends here)
+                    const uint32_t cls = lane & 15u;
+                    const uint32_t n_words = (nthr >> 4) * (uint32_t)QF_MASK_WORDS;   // words of my class
+                    uint64_t cur = 0;        // survivors left in the word I hold
+                    uint32_t cur_col = tid, cur_base = 0;
+                    bool dry = false;        // the pool of my class is exhausted
+                    while (true) {
+                        while (cur == 0 && !dry) {
+                            const uint32_t idx = atomicAdd(&s_pool[cls], 1u);
+                            if (idx >= n_words) { dry = true; break; }
+                            const uint32_t x = idx % (uint32_t)QF_MASK_WORDS;
+                            cur_col = cls + 16u * (idx / (uint32_t)QF_MASK_WORDS);
+                            cur_base = 64u * x;
+                            cur = s_surv[x * nthr + cur_col];
                         }
+                        if (!__any_sync(FULL_MASK, cur != 0)) break;
+                        uint32_t li0 = bn, li1 = bn;   // bn: the all-padding dummy row
+                        if (cur) { li0 = cur_base + (uint32_t)__ffsll((long long)cur) - 1u; cur &= cur - 1; }
+                        if (cur) { li1 = cur_base + (uint32_t)__ffsll((long long)cur) - 1u; cur &= cur - 1; }
+                        const unsigned char *column = reinterpret_cast<const unsigned char *>(s_pm + cur_col);
+                        const uint32_t mm = s_plen[cur_col];
+                        const uint32_t rr = p.r_begin + rb * nthr + cur_col;
+                        const uint32_t n0 = li0 < bn ? s_len[li0] : 0u, n1 = li1 < bn ? s_len[li1] : 0u;
+                        const uint32_t trip = __reduce_max_sync(FULL_MASK, max(n0, n1));
+                        const uint2 *ta = reinterpret_cast<const uint2 *>(s_chr + li0 * stride);
+                        const uint2 *tb = reinterpret_cast<const uint2 *>(s_chr + li1 * stride);
+                        uint64_t Sa[W], Sb[W];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            step(Sa, __byte_perm(wa.y, 0u, 0x4440u + q));
-                            step(Sb, __byte_perm(wb.y, 0u, 0x4440u + q));
+                        for (int x = 0; x < W; ++x) Sa[x] = Sb[x] = ~0ull;
+                        for (uint32_t j = 0; j < trip; j += 8) {
+                            const uint2 wa = ta[j >> 3], wb = tb[j >> 3];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                step(Sa, __byte_perm(wa.x, 0u, 0x4440u + q), column);
+                                step(Sb, __byte_perm(wb.x, 0u, 0x4440u + q), column);
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                step(Sa, __byte_perm(wa.y, 0u, 0x4440u + q), column);
+                                step(Sb, __byte_perm(wb.y, 0u, 0x4440u + q), column);
+                            }
                         }
-                    }
-                    uint32_t lcs0 = 0, lcs1 = 0;
+                        uint32_t lcs0 = 0, lcs1 = 0;
 #pragma unroll
-                    for (int x = 0; x < W; ++x) { lcs0 += __popcll(~Sa[x]); lcs1 += __popcll(~Sb[x]); }
+                        for (int x = 0; x < W; ++x) { lcs0 += __popcll(~Sa[x]); lcs1 += __popcll(~Sb[x]); }
 #pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        const uint32_t li = q ? li1 : li0, n = q ? n1 : n0, lcs = q ? lcs1 : lcs0;
-                        // score >= threshold  <=>  dist <= dmax[m + n]  (the table is built with the score's map)
-                        const bool keep = li < bn && (int)(m + n - 2u * lcs) <= (int)s_dmax[li < bn ? m + n : 0u];
-                        double score = 0.0;
-                        if (keep) {
-                            score = qratio_from_lcs(m, n, lcs);
-                            // compare_terms on K = 1 items: one step, weight 1/2
-                            if (!flat) score = __fma_rn(score, 0.5, 0.0);
+                        for (int q = 0; q < 2; ++q) {
+                            const uint32_t li = q ? li1 : li0, n = q ? n1 : n0, lcs = q ? lcs1 : lcs0;
+                            // score >= threshold  <=>  dist <= dmax[m + n]  (the table is built with the score's map)
+                            const bool keep = li < bn && (int)(mm + n - 2u * lcs) <= (int)s_dmax[li < bn ? mm + n : 0u];
+                            double score = 0.0;
+                            if (keep) {
+                                score = qratio_from_lcs(mm, n, lcs);
+                                // compare_terms on K = 1 items: one step, weight 1/2
+                                if (!flat) score = __fma_rn(score, 0.5, 0.0);
+                            }
+                            emit_pairs(keep, p.swap_out ? rr : l0 + li, p.swap_out ? l0 + li : rr, score, out,
+                                       p.job.out_capacity, count, p.job.out_flags);
                         }
-                        emit_pairs(keep, p.swap_out ? r : l0 + li, p.swap_out ? l0 + li : r, score, out,
-                                   p.job.out_capacity, count, p.job.out_flags);
                     }
                 }
                 b0 += bn;
