@@ -316,7 +316,7 @@ class DeviceStringPacker:
             k = np.fromiter((len(lv) for lv in s), dtype=np.int64, count=len(s))
             strs = [x for lv in s for x in lv]
             raw_len = np.fromiter((len(x) for x in strs), dtype=np.int64, count=len(strs))
-            cps = np.frombuffer("".join(strs).encode("utf-32-le"), dtype=np.uint32)
+            cps = np.frombuffer("".join(strs).encode("utf-32-le", "surrogatepass"), dtype=np.uint32)
             if len(cps) >= 2 ** 32:
                 raise PackError("more than 2^32 characters on one side")
             counts = np.bincount(cps) if len(cps) else np.zeros(0, dtype=np.int64)

@@ -509,8 +509,6 @@ class Engine:
         copy, and the step ends when the last kernel does.  Smaller jobs take one launch into a
         device arena and one copy.  An arena that turns out too small is counted exactly by the
         kernel and that block is run again."""
-        import time
-
         stream = torch.cuda.current_stream(self.device)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
@@ -642,7 +640,7 @@ class Engine:
 
         # ---- phase 2: host regions for everything, then the rests straight into them ----
         align = lambda x: (x + 255) & ~255   # noqa: E731
-        layout, need = [], 0
+        need = 0
         for j in live:
             job, pl = jobs[j], plans[j]
             count, flags, stats, n_exc = pl["first"]
@@ -718,8 +716,6 @@ class Engine:
                 infos[j]["d2h_bytes"] += n_bytes + n_exc * 16 + (dict_bytes if "dict" in pl else 0)
                 account(infos[j], count, flags, stats, n_exc, mode)
 
-        slots = {}
-        n_slot = 0
         pending = [(j, blk) for j in live if plans[j]["big"] for blk in plans[j]["rest"]]
         while pending:
             ctl_rest = self._arena("ctl_rest", 64 * len(pending), pinned=False)

@@ -547,7 +547,7 @@ def pack_strings(*sides: Sequence[Sequence[str]]) -> List[PackedStrings]:
         class_end = np.searchsorted(words[perm], np.arange(1, WORD_CLASSES + 1), side="right")
         strs = [x for i in perm for x in s[i]]
         lens = np.fromiter((len(x) for x in strs), dtype=np.int64, count=len(strs))
-        cps = np.frombuffer("".join(strs).encode("utf-32-le"), dtype=np.uint32)
+        cps = np.frombuffer("".join(strs).encode("utf-32-le", "surrogatepass"), dtype=np.uint32)
         per_side.append((k[perm], lens, cps, perm, class_end))
     sets = [np.unique(c[2]) for c in per_side]
     common = np.unique(np.concatenate(sets)) if sets else np.zeros(0, dtype=np.uint32)
