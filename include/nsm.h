@@ -203,6 +203,15 @@ int nsm_qratio_allpairs(const nsm_strings_t *left, const nsm_strings_t *right, c
  * device->host copy engine.  host_dst: page-locked host memory (device-accessible under UVA). */
 int nsm_publish(const void *dev_src, void *host_dst, uint32_t bytes, void *stream);
 
+/* Host-side decoders of the compact record formats (plain CPU loops, no GPU involved: the host
+ * half of NSM_OUT_PACKETS / NSM_OUT_CODED for any binding).  `out` (host memory) must hold the sum
+ * of the packets' counts; `left_perm` / `right_perm` (or NULL) map the stored positions in the
+ * records to the caller's item indices.  Return the number of records written. */
+uint64_t nsm_decode_packets(const nsm_packet_t *packets, uint64_t n_packets, const uint32_t *left_perm,
+                            const uint32_t *right_perm, nsm_pair_t *out);
+uint64_t nsm_decode_cpackets(const nsm_cpacket_t *packets, uint64_t n_packets, const uint64_t *dict,
+                             const uint32_t *left_perm, const uint32_t *right_perm, nsm_pair_t *out);
+
 /* Marks every slot of a score dictionary (NSM_OUT_CODED, uint64[NSM_DICT_SLOTS]) free. */
 int nsm_dict_reset(uint64_t *dict, void *stream);
 

@@ -135,3 +135,40 @@ extern "C" int nsm_publish(const void *dev_src, void *host_dst, uint32_t bytes, 
     NSM_CUDA_CHECK(cudaGetLastError());
     return NSM_OK;
 }
+
+// ---- host side of the compact record formats ---------------------------------------------------
+extern "C" uint64_t nsm_decode_packets(const nsm_packet_t *packets, uint64_t n_packets,
+                                       const uint32_t *left_perm, const uint32_t *right_perm,
+                                       nsm_pair_t *out) {
+    uint64_t n = 0;
+    for (uint64_t i = 0; i < n_packets; ++i) {
+        const nsm_packet_t &pk = packets[i];
+        const uint32_t cnt = pk.count < NSM_PACKET_RECORDS ? pk.count : NSM_PACKET_RECORDS;
+        for (uint32_t k = 0; k < cnt; ++k, ++n) {
+            const uint32_t l = pk.left0 + (pk.local[k] >> 7), r = pk.right0 + (pk.local[k] & 127u);
+            out[n].left = left_perm ? left_perm[l] : l;
+            out[n].right = right_perm ? right_perm[r] : r;
+            out[n].score = pk.score[k];
+        }
+    }
+    return n;
+}
+
+extern "C" uint64_t nsm_decode_cpackets(const nsm_cpacket_t *packets, uint64_t n_packets, const uint64_t *dict,
+                                        const uint32_t *left_perm, const uint32_t *right_perm,
+                                        nsm_pair_t *out) {
+    uint64_t n = 0;
+    for (uint64_t i = 0; i < n_packets; ++i) {
+        const nsm_cpacket_t &pk = packets[i];
+        const uint32_t cnt = pk.count < NSM_CPACKET_RECORDS ? pk.count : NSM_CPACKET_RECORDS;
+        for (uint32_t k = 0; k < cnt; ++k, ++n) {
+            const uint32_t rec = pk.rec[k];
+            const uint32_t l = pk.left0 + ((rec & 0xffffu) >> 7), r = pk.right0 + (rec & 127u);
+            out[n].left = left_perm ? left_perm[l] : l;
+            out[n].right = right_perm ? right_perm[r] : r;
+            uint64_t bits = dict[rec >> 16];
+            memcpy(&out[n].score, &bits, sizeof(double));
+        }
+    }
+    return n;
+}

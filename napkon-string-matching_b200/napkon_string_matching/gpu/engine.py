@@ -75,19 +75,17 @@ class Records:
         """All parts as one ``PAIR_DTYPE`` array with the callers' item indices."""
         if not self.parts:
             return np.zeros(0, dtype=PAIR_DTYPE)
-        arrays = [nsmlib.decode_packets(a) if mode == nsmlib.OUT_PACKETS else
-                  nsmlib.decode_cpackets(a, self.dictionary) if mode == nsmlib.OUT_CODED else a
-                  for mode, a in self.parts]
-        if len(arrays) == 1:
-            plain = self.parts[0][0] == nsmlib.OUT_PAIRS
-            out = arrays[0].copy() if (plain and (copy or self.left_perm is not None)) else arrays[0]
-        else:
-            out = np.concatenate(arrays)
-        if self.left_perm is not None:   # stored positions -> the caller's item indices
-            out["left"] = self.left_perm[out["left"]]
-        if self.right_perm is not None:
-            out["right"] = self.right_perm[out["right"]]
-        return out
+        if len(self.parts) == 1 and self.parts[0][0] == nsmlib.OUT_PAIRS and self.left_perm is None \
+                and self.right_perm is None:
+            return self.parts[0][1].copy() if copy else self.parts[0][1]
+        # one pass per part through the library's host decoders (packets -> 16-byte records, the
+        # stored-position -> item-index maps applied on the way)
+        total = sum(len(a) * nsmlib.ENTRY_RECORDS[mode] for mode, a in self.parts)
+        out = np.empty(total, dtype=PAIR_DTYPE)
+        pos = 0
+        for mode, a in self.parts:
+            pos += nsmlib.decode_into(out[pos:], mode, a, self.dictionary, self.left_perm, self.right_perm)
+        return out[:pos]
 
 
 class Engine:

@@ -62,6 +62,36 @@ def decode_cpackets(packets: np.ndarray, dictionary: np.ndarray) -> np.ndarray:
     out["score"] = np.ascontiguousarray(dictionary).view(np.float64)[rec >> np.uint32(16)]
     return out
 
+def _perm_ptr(perm, keep):
+    if perm is None:
+        return None
+    perm = np.ascontiguousarray(perm, dtype=np.uint32)
+    keep.append(perm)
+    return perm.ctypes.data
+
+
+def decode_into(out: np.ndarray, mode: int, part: np.ndarray, dictionary=None, left_perm=None,
+                right_perm=None) -> int:
+    """Decodes one wire-format part into the head of ``out`` (contiguous ``PAIR_DTYPE``) with the
+    library's host decoders (nsm_decode_*: one pass, the item permutations applied on the way);
+    returns the number of records written."""
+    lib, keep = load(), []
+    lp, rp = _perm_ptr(left_perm, keep), _perm_ptr(right_perm, keep)
+    part = np.ascontiguousarray(part)
+    if mode == OUT_PACKETS:
+        return int(lib.nsm_decode_packets(part.ctypes.data, len(part), lp, rp, out.ctypes.data))
+    if mode == OUT_CODED:
+        table = np.ascontiguousarray(dictionary, dtype=np.uint64)
+        return int(lib.nsm_decode_cpackets(part.ctypes.data, len(part), table.ctypes.data, lp, rp, out.ctypes.data))
+    n = len(part)
+    out[:n] = part
+    if left_perm is not None:
+        out["left"][:n] = np.asarray(left_perm)[part["left"]]
+    if right_perm is not None:
+        out["right"][:n] = np.asarray(right_perm)[part["right"]]
+    return n
+
+
 RAW_SUFFIX_PARTS, RAW_LEVELS = 0, 1
 PACK_MAX_ITEM_IDS = 1024
 PACK_FLAG_TOO_LARGE, PACK_FLAG_NOT_NESTED, PACK_FLAG_BAD_ID = 1, 2, 4
@@ -69,7 +99,7 @@ PACK_FLAG_TOO_LARGE, PACK_FLAG_NOT_NESTED, PACK_FLAG_BAD_ID = 1, 2, 4
 EXPORTS = ("nsm_version", "nsm_last_error", "nsm_last_launch_count", "nsm_jaccard_allpairs",
            "nsm_qratio_allpairs", "nsm_microbench", "nsm_pack_count_ids", "nsm_pack_scratch_bytes",
            "nsm_pack_sets_measure", "nsm_pack_sets_fill", "nsm_dict_reset", "nsm_publish",
-           "nsm_pack_strings_measure", "nsm_pack_strings_fill")
+           "nsm_pack_strings_measure", "nsm_pack_strings_fill", "nsm_decode_packets", "nsm_decode_cpackets")
 STR_SYM_NONE, STR_FLAG_UNMAPPED = 0xffff, 1
 
 
@@ -162,6 +192,10 @@ def load() -> C.CDLL:
     lib.nsm_pack_strings_fill.argtypes = [C.POINTER(NsmRawStrings), C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
                                           C.c_void_p]
+    lib.nsm_decode_packets.restype = C.c_uint64
+    lib.nsm_decode_packets.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.nsm_decode_cpackets.restype = C.c_uint64
+    lib.nsm_decode_cpackets.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
 

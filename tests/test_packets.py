@@ -58,6 +58,52 @@ def test_decode_cpackets_on_hand_built_packets():
     assert [(int(a), int(b), float(c)) for a, b, c in zip(out["left"], out["right"], out["score"])] == want
 
 
+@pytest.mark.parametrize("mode", [nsmlib.OUT_PAIRS, nsmlib.OUT_PACKETS, nsmlib.OUT_CODED])
+def test_library_host_decoders_equal_the_numpy_decoders(mode):
+    """nsm_decode_packets / nsm_decode_cpackets (plain CPU loops inside the library; no GPU needed)
+    against the numpy decoders, with and without the stored-position -> item-index maps, on full,
+    partial and empty packets; Records.decode goes through them."""
+    from napkon_string_matching.gpu.engine import Records
+
+    rng = np.random.default_rng(40 + mode)
+    n = 513
+    table = rng.random(nsmlib.DICT_SLOTS).view(np.uint64)
+    if mode == nsmlib.OUT_PAIRS:
+        part = np.zeros(n, dtype=nsmlib.PAIR_DTYPE)
+        part["left"], part["right"], part["score"] = rng.integers(0, 5000, n), rng.integers(0, 4000, n), rng.random(n)
+        want = part.copy()
+    else:
+        dt, cap = (nsmlib.PACKET_DTYPE, nsmlib.PACKET_RECORDS) if mode == nsmlib.OUT_PACKETS else \
+            (nsmlib.CPACKET_DTYPE, nsmlib.CPACKET_RECORDS)
+        part = np.zeros(n, dtype=dt)
+        part["left0"], part["right0"] = rng.integers(0, 9, n) * 512, rng.integers(0, 31, n) * 128
+        part["count"] = np.where(rng.random(n) < 0.7, cap, rng.integers(0, cap + 1, n))
+        if mode == nsmlib.OUT_PACKETS:
+            part["score"], part["local"] = rng.random((n, cap)), rng.integers(0, 1 << 16, (n, cap))
+            want = nsmlib.decode_packets(part)
+        else:
+            part["rec"] = rng.integers(0, 1 << 32, (n, cap), dtype=np.uint64).astype(np.uint32)
+            want = nsmlib.decode_cpackets(part, table)
+    out = np.empty(len(part) * nsmlib.ENTRY_RECORDS[mode] + 7, dtype=nsmlib.PAIR_DTYPE)
+    m = nsmlib.decode_into(out, mode, part, table)
+    assert m == len(want) and np.array_equal(out[:m], want)
+    lperm, rperm = rng.permutation(5200).astype(np.uint32), rng.permutation(4100).astype(np.uint32)
+    mapped = want.copy()
+    mapped["left"], mapped["right"] = lperm[want["left"]], rperm[want["right"]]
+    m = nsmlib.decode_into(out, mode, part, table, lperm, rperm)
+    assert m == len(want) and np.array_equal(out[:m], mapped)
+    assert nsmlib.decode_into(out, mode, part[:0], table) == 0
+    # Records: several parts of different formats in one result
+    pairs = np.zeros(5, dtype=nsmlib.PAIR_DTYPE)
+    pairs["left"], pairs["right"], pairs["score"] = np.arange(5), np.arange(5) + 10, np.arange(5) / 8
+    rec = Records([(mode, part), (nsmlib.OUT_PAIRS, pairs)], len(want) + 5, lperm, rperm, table)
+    got = rec.decode()
+    tail = pairs.copy()
+    tail["left"], tail["right"] = lperm[pairs["left"]], rperm[pairs["right"]]
+    assert np.array_equal(got, np.concatenate([mapped, tail]))
+    assert np.array_equal(Records([(nsmlib.OUT_PAIRS, pairs)], 5).decode(copy=False), pairs)
+
+
 def _tokenid_packs(nl, nr):
     lens, flat = syn.token_id_level_sets(nl, syn.SEED_LEFT)
     pl = pack.pack_suffix_id_sets(lens, flat, 30000)
