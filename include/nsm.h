@@ -212,6 +212,12 @@ uint64_t nsm_decode_packets(const nsm_packet_t *packets, uint64_t n_packets, con
 uint64_t nsm_decode_cpackets(const nsm_cpacket_t *packets, uint64_t n_packets, const uint64_t *dict,
                              const uint32_t *left_perm, const uint32_t *right_perm, nsm_pair_t *out);
 
+/* Host-side: sorts `n` records by (left, right) — the row-major order of the cross product, the
+ * order of the reference's result frame (comparable_data.py:191) — into `sorted` (host memory, n
+ * records, must not overlap `records`): counting sort by left, then each left row by right.
+ * Every left index must be < n_left.  Returns 0, or NSM_ERR_BAD_ARG. */
+int nsm_sort_pairs(const nsm_pair_t *records, uint64_t n, uint32_t n_left, nsm_pair_t *sorted);
+
 /* Marks every slot of a score dictionary (NSM_OUT_CODED, uint64[NSM_DICT_SLOTS]) free. */
 int nsm_dict_reset(uint64_t *dict, void *stream);
 

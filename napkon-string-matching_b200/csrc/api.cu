@@ -1,5 +1,7 @@
 // Entry points that are not kernels: version, error text, job validation, device facts.
+#include <algorithm>
 #include <atomic>
+#include <vector>
 #include <math.h>
 #include <stdarg.h>
 #include <string.h>
@@ -171,4 +173,27 @@ extern "C" uint64_t nsm_decode_cpackets(const nsm_cpacket_t *packets, uint64_t n
         }
     }
     return n;
+}
+
+extern "C" int nsm_sort_pairs(const nsm_pair_t *records, uint64_t n, uint32_t n_left, nsm_pair_t *sorted) {
+    if ((n && (!records || !sorted)) || (records && sorted && records == sorted)) {
+        nsm::set_error("nsm_sort_pairs: null or overlapping buffers");
+        return NSM_ERR_BAD_ARG;
+    }
+    std::vector<uint64_t> start((size_t)n_left + 1, 0);
+    for (uint64_t i = 0; i < n; ++i) {
+        if (records[i].left >= n_left) {
+            nsm::set_error("nsm_sort_pairs: left index %u >= n_left %u", records[i].left, n_left);
+            return NSM_ERR_BAD_ARG;
+        }
+        ++start[(size_t)records[i].left + 1];
+    }
+    for (size_t l = 0; l < n_left; ++l) start[l + 1] += start[l];
+    std::vector<uint64_t> fill(start.begin(), start.end() - 1);
+    for (uint64_t i = 0; i < n; ++i) sorted[fill[records[i].left]++] = records[i];
+    for (size_t l = 0; l < n_left; ++l)
+        if (start[l + 1] - start[l] > 1)
+            std::sort(sorted + start[l], sorted + start[l + 1],
+                      [](const nsm_pair_t &a, const nsm_pair_t &b) { return a.right < b.right; });
+    return NSM_OK;
 }

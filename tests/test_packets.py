@@ -104,6 +104,20 @@ def test_library_host_decoders_equal_the_numpy_decoders(mode):
     assert np.array_equal(Records([(nsmlib.OUT_PAIRS, pairs)], 5).decode(copy=False), pairs)
 
 
+def test_library_sort_pairs_is_the_row_major_order():
+    rng = np.random.default_rng(77)
+    n, n_left, n_right = 20000, 300, 5000
+    key = rng.choice(n_left * n_right, size=n, replace=False)
+    rec = np.zeros(n, dtype=nsmlib.PAIR_DTYPE)
+    rec["left"], rec["right"], rec["score"] = key // n_right, key % n_right, rng.random(n)
+    got = nsmlib.sort_pairs(rec, n_left)
+    assert np.array_equal(got, rec[np.lexsort((rec["right"], rec["left"]))])
+    assert len(nsmlib.sort_pairs(rec[:0], n_left)) == 0
+    assert np.array_equal(nsmlib.sort_pairs(rec[:1], n_left), rec[:1])
+    with pytest.raises(nsmlib.NsmError):
+        nsmlib.sort_pairs(rec, int(rec["left"].max()))      # a left index beyond n_left
+
+
 def _tokenid_packs(nl, nr):
     lens, flat = syn.token_id_level_sets(nl, syn.SEED_LEFT)
     pl = pack.pack_suffix_id_sets(lens, flat, 30000)
