@@ -24,6 +24,11 @@ With the default workload the line also carries `secondary`: BASELINE configs[4]
 `--impl reference` times the UNMODIFIED reference's own `gen_comparable` (oracle/_ref, a copy of
 /root/reference made by oracle/make_ref.py; nltk / rapidfuzz shimmed) on all host cores, on a
 bounded sample of the same workload; without oracle/_ref it falls back to the oracle port.
+
+The cohorts are stored the way the product path stores them (pack.chunked_level_order: items of one
+level count in chunks of the kernel's unit).  Experiment switches (not used by the driver):
+NSM_BENCH_ITEM_ORDER=drawn|sorted (other storage orders), NSM_BENCH_TRACE_TIMED=1 (+
+NSM_BENCH_TRACE_DIR) records the engine's host-side marks of the timed end-to-end steps per rank.
 """
 from __future__ import annotations
 
