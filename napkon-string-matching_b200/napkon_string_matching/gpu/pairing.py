@@ -295,10 +295,12 @@ def result_frame(records: np.ndarray, left_df: pd.DataFrame, right_df: pd.DataFr
     li = records["left"].astype(np.int64)
     ri = records["right"].astype(np.int64)
     index = li * len(right_df) + ri
+    # gather with the columns' own arrays (take keeps the dtype — Arrow-backed strings stay Arrow:
+    # going through object arrays made pandas re-infer every gathered column, 3/4 of the time)
     data = {}
     for c in lcols:
-        data[left_prefix + c] = left_df[c].to_numpy()[li] if len(li) else left_df[c].to_numpy()[:0]
+        data[left_prefix + c] = left_df[c].array.take(li)
     for c in rcols:
-        data[right_prefix + c] = right_df[c].to_numpy()[ri] if len(ri) else right_df[c].to_numpy()[:0]
+        data[right_prefix + c] = right_df[c].array.take(ri)
     data[Columns.MATCH_SCORE.value] = records["score"].astype(np.float64)
     return pd.DataFrame(data, index=pd.Index(index))
