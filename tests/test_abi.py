@@ -41,6 +41,7 @@ def test_struct_layouts_match_the_header():
     assert nsmlib.NsmJob.out_mode.offset == 80
     assert nsmlib.PACKET_DTYPE.itemsize == 496 and nsmlib.PACKET_DTYPE.fields["local"][1] == 400
     assert ctypes.sizeof(nsmlib.NsmRawSets) == 4 * 8 + 6 * 4
+    assert ctypes.sizeof(nsmlib.NsmRawStrings) == 3 * 8 + 4 * 4 and nsmlib.NsmRawStrings.blank_sym.offset == 36
     assert nsmlib.PAIR_DTYPE.itemsize == 16
     assert nsmlib.PAIR_DTYPE.fields["score"][1] == 8
 
