@@ -14,6 +14,7 @@ the middle.  Tokenisation runs once per item on the host, never per pair.
 from __future__ import annotations
 
 import logging
+from bisect import insort
 import re
 from functools import lru_cache
 from typing import Iterable, List
@@ -215,17 +216,45 @@ def gen_comp_value(items) -> List[List[str]]:
     return [tokenize(items[-i:]) for i in range(1, len(items) + 1)]
 
 
+_PART_WORDS: dict = {}          # text of a part -> its kept (casefold, word) pairs, or None: not simple
+_PART_WORDS_CAP = 1 << 20       # distinct parts remembered (columns repeat their parts: ids, headers)
+_MISS = object()
+
+
+def _part_words(text):
+    """The words of one simple part that survive the stop-word / punctuation filter, as
+    (casefold, word) pairs in the order of the text; None when the part is not a simple str."""
+    if not isinstance(text, str):
+        return None
+    if _is_simple(text):
+        stops = stop_words("german")
+        hit = tuple((w.casefold(), w) for w in text.split()
+                    if w.casefold() not in stops and w not in PREPARE_REMOVE_SYMBOLS)
+    else:
+        hit = None
+    if len(_PART_WORDS) < _PART_WORDS_CAP:
+        _PART_WORDS[text] = hit
+    return hit
+
+
 def _gen_comp_value_simple(items):
-    stops = stop_words("german")
-    kept: set = set()                                  # (casefold, word): sorts without a key call
+    kept: set = set()            # (casefold, word) of the suffix so far ...
+    ordered: list = []           # ... and the same pairs in sorted order (they sort without a key call)
     levels = []
+    cached = _PART_WORDS.get
     for part in reversed(items):                       # the part that enters at the next level
-        for text in (part if isinstance(part, list) else (part,)):
-            if not isinstance(text, str) or not _is_simple(text):
+        for text in (part if part.__class__ is list else (part,)):
+            try:
+                words = cached(text, _MISS)
+            except TypeError:                          # an unhashable cell
                 return None
-            for w in text.split():
-                folded = w.casefold()
-                if folded not in stops and w not in PREPARE_REMOVE_SYMBOLS:
-                    kept.add((folded, w))
-        levels.append([w for _, w in sorted(kept)])
+            if words is _MISS:
+                words = _part_words(text)
+            if words is None:
+                return None
+            for fw in words:
+                if fw not in kept:
+                    kept.add(fw)
+                    insort(ordered, fw)
+        levels.append([w for _, w in ordered])
     return levels
